@@ -1,0 +1,192 @@
+/*
+ * spx_b200.h — C ABI of libspx_b200.so: the B200 (sm_100a) tableau pivot loop.
+ *
+ * The reference (jqnfxa/Simplex-Method-Solver) is pure Python and has no FFI;
+ * its boundary for this path is the Python surface of src/simplex.py.  Each
+ * entry point below names the reference code it replaces (file:line into
+ * /root/reference/src/).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (text: spx_last_error());
+ *   - all pointers named d_* are DEVICE pointers (plain void* / double* taken
+ *     from any allocator, e.g. torch.Tensor.data_ptr()); h_* are HOST pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - nothing allocates behind the caller's back;
+ *   - all arithmetic is IEEE binary64 with separately rounded mul/sub/div
+ *     (no FMA contraction, no reciprocal multiply) so results are bit-identical
+ *     to CPython floats (simplex.py:156,160,163,173-175).
+ *
+ * Device data layouts
+ *   "reference flat"  the reference's ragged table flattened row-major: n rows
+ *                     of m+1 cells [a_1..a_m, b] then the f row with m cells
+ *                     (simplex.py:36-39); cells = n*(m+1)+m.  Used by the
+ *                     batched small-LP solver and by import/export.
+ *   "split"           used by the streaming solver for large tableaus:
+ *                     body  A[(n+1)][ld]  row-major, columns 0..m-1, row n = f,
+ *                           ld = spx_ld(m) (multiple of 16 doubles => every row
+ *                           starts on a 128-byte line, m+1 = 32769 would not);
+ *                     rhs   b[n] contiguous (the '-b' column), kept separate so
+ *                           the body is a clean m-wide stream and, when the
+ *                           body is column-sharded over GPUs, b is replicated.
+ *   colbuf            the gathered pivot column, spx_colbuf_doubles(n) doubles
+ *                     (n+1 cells, f row last, padded to a whole row tile).
+ *   labels            int32 codes instead of the reference's strings
+ *                     (simplex.py:30-33): x_j -> j-1, y_i -> m+i-1; rowlab[m]
+ *                     is the header over the columns, collab[n] labels the rows.
+ */
+#ifndef SPX_B200_H
+#define SPX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPX_ABI_VERSION 1
+
+/* status codes == the outcomes of pick_element(), simplex.py:70-141 */
+#define SPX_PIVOT       1   /* (True, r, c, e)                                   :91,:141 */
+#define SPX_OPTIMAL     0   /* (False, x1, x2, f)                                :101-103 */
+#define SPX_INCORRECT  -1   /* ValueError("incorrect system")                    :88-89   */
+#define SPX_NOCONV     -2   /* ValueError("simplex method does not converge")    :138-139 */
+#define SPX_CAP        -3   /* max_pivots reached; the reference has no cap and cycles    */
+
+/* pivoting rules */
+#define SPX_RULE_REFERENCE 0  /* first-negative entering, max-negative-ratio leaving (the reference) */
+#define SPX_RULE_DANTZIG   1  /* most-negative entering (lowest index on ties); leaving as reference */
+
+/* Device-resident solver state, 128 bytes.  Written by the pick kernels, read
+ * by the update kernels, so a whole chunk of pivots can be enqueued with no host
+ * round trip; once status != SPX_PIVOT every later kernel of the chunk is a no-op. */
+typedef struct spx_state {
+    int32_t status;       /* outcome of the most recent pick (SPX_PIVOT while running)  */
+    int32_t r;            /* pivot row    (valid when status == SPX_PIVOT)              */
+    int64_t c;            /* pivot column (GLOBAL index when column-sharded)            */
+    double  p;            /* pivot value T[r][c]                                        */
+    int64_t npiv;         /* pivots applied so far                                      */
+    int64_t max_pivots;   /* cap; pick reports SPX_CAP when npiv has reached it         */
+    int32_t phase1;       /* 1 when the pivot came from the '-b' branch (:79-91)        */
+    int32_t slot;         /* hint slot the next update fills = (npiv+1)&1               */
+    /* fused pricing: while update k writes the new f row and b column it also
+     * min-reduces the first negative index of each into hint_*[slot]; the next
+     * pick uses them when hint_tag[npiv&1] == npiv, else it scans.              */
+    int64_t hint_tag[2];
+    int32_t hint_bneg[2]; /* first i with b[i] < 0, INT32_MAX none                      */
+    int32_t hint_fneg[2]; /* first LOCAL j with f[j] < 0, INT32_MAX none                */
+    int64_t reserved[6];
+} spx_state;
+
+/* ---- library ----------------------------------------------------------- */
+int         spx_version(void);               /* SPX_ABI_VERSION */
+const char *spx_last_error(void);            /* thread-local text of the last failure */
+int64_t     spx_ld(int64_t m);               /* leading dimension (doubles) of a split body of m columns */
+int64_t     spx_cells(int32_t n, int32_t m); /* n*(m+1)+m */
+int64_t     spx_colbuf_doubles(int32_t n);   /* capacity a pivot-column buffer needs */
+int         spx_state_bytes(void);           /* sizeof(spx_state) */
+int         spx_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+/* kernels of this library launched since the last call with reset != 0 (bench.py's gpu_launches) */
+int64_t     spx_launch_count(int reset);
+
+/* ---- layout conversion (SimplexMethod.__init__, simplex.py:25-39) -------- */
+/* src is reference-flat, host or device (cudaMemcpyDefault); dst is split; the
+ * padding columns of d_A are zeroed. */
+int spx_import_table(const double *src_flat, double *d_A, double *d_b,
+                     int32_t n, int32_t m, int64_t ld, void *stream);
+/* Column block [col0, col0+m_loc) of a reference-flat table -> a local split
+ * body d_A[(n+1)][ld_loc] (+ b when d_b != NULL): the loader of one column shard. */
+int spx_import_shard(const double *src_flat, double *d_A, double *d_b,
+                     int32_t n, int32_t m, int64_t col0, int32_t m_loc, int64_t ld_loc,
+                     void *stream);
+/* split -> reference-flat (host or device destination): what Info.table /
+ * SimplexMethod.table expose (simplex.py:16,36-39). */
+int spx_export_table(const double *d_A, const double *d_b, double *dst_flat,
+                     int32_t n, int32_t m, int64_t ld, void *stream);
+/* state = {running, npiv 0, cap}, labels x1..xm / y1..yn (simplex.py:30-33) */
+int spx_init_state(spx_state *d_state, int32_t *d_rowlab, int32_t *d_collab,
+                   int32_t n, int32_t m, int64_t max_pivots, void *stream);
+
+/* ---- K1 + K2: pick_element(), simplex.py:70-141 -------------------------- */
+/* Selects the pivot of the split tableau (d_A, d_b); writes *d_state and gathers
+ * the pivot column (n+1 doubles, f row last) into d_colbuf for spx_update.
+ * sticky != 0: do nothing when d_state->status is already terminal (used by
+ * pre-enqueued chunks). */
+int spx_pick(const double *d_A, const double *d_b, int32_t n, int32_t m, int64_t ld,
+             int32_t rule, int32_t sticky, spx_state *d_state, double *d_colbuf, void *stream);
+
+/* ---- K3: recalculate_matrix(), simplex.py:149-177 ------------------------ */
+/* Out-of-place dictionary pivot (the reference deep-copies, :149): reads
+ * (d_Ain, d_bin), writes (d_Aout, d_bout); swaps labels rowlab[c] <-> collab[r]
+ * (:152), appends (r, c) to d_trace[npiv] (may be NULL) and increments npiv.
+ * No-op unless d_state->status == SPX_PIVOT.  16 B of HBM traffic per cell. */
+int spx_update(const double *d_Ain, double *d_Aout, const double *d_bin, double *d_bout,
+               int32_t n, int32_t m, int64_t ld, spx_state *d_state,
+               const double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab,
+               int32_t *d_trace, void *stream);
+
+/* ---- the loop of get_solution(), simplex.py:179-199 / :261-269 ----------- */
+/* Device-side loop over ping-pong buffers (A0,b0) <-> (A1,b1); the current
+ * table is in buffer (npiv & 1) where npiv is read from d_state.  Enqueues
+ * pick+update pairs in chunks of `chunk` pivots with no host round trip, then
+ * reads the state back; stops on a terminal status, at d_state->max_pivots
+ * (SPX_CAP), or after `stop_after` further pivots (status stays SPX_PIVOT;
+ * <= 0: no such limit).  d_trace is [max_pivots][2] int32 or NULL.
+ * On return *h_status / *h_npiv mirror d_state. */
+int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1,
+              int32_t n, int32_t m, int64_t ld, int32_t rule,
+              spx_state *d_state, double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab,
+              int32_t *d_trace, int32_t chunk, int64_t stop_after,
+              int32_t *h_status, int64_t *h_npiv, void *stream);
+
+/* ---- find_optimum() / f(), simplex.py:48-68, generalised to m variables --- */
+/* d_x[j] = b of the row labelled x_{j+1}, else 0; d_obj[0] = function[0]*x1 +
+ * function[1]*x2 exactly as :49 (0 when m < 2); d_obj[1] = sum_j function[j]*x[j]
+ * accumulated left to right. */
+int spx_extract(const double *d_b, int32_t n, int32_t m, const int32_t *d_collab,
+                const double *d_function, double *d_x, double *d_obj, void *stream);
+
+/* ---- K4: batches of independent small LPs, one warp per LP ---------------- */
+/* d_T is [B][cells] reference-flat, solved IN PLACE (final tables left in d_T).
+ * Outputs (device, any may be NULL except status/npiv):
+ *   d_x [B][m], d_obj [B] (function[0]*x1+function[1]*x2, simplex.py:49),
+ *   d_status [B], d_npiv [B], d_rowlab [B][m], d_collab [B][n],
+ *   d_trace [B][max_pivots][2], d_snap [B][max_pivots+1][cells] (the Info.table
+ *   sequence of get_solution(), simplex.py:181,198: slot k = table before pivot k).
+ * cells is limited by shared memory: spx_batched_max_cells(). */
+int spx_solve_batched(double *d_T, int64_t B, int32_t n, int32_t m, int32_t rule,
+                      int32_t max_pivots, double *d_x, double *d_obj,
+                      int32_t *d_status, int32_t *d_npiv,
+                      int32_t *d_rowlab, int32_t *d_collab,
+                      int32_t *d_trace, double *d_snap, void *stream);
+int64_t spx_batched_max_cells(void);
+
+/* ---- column-sharded large tableau (one process per GPU) ------------------- */
+/* Rank g owns global columns [col0, col0+m_loc) of the body as a local split
+ * matrix d_A[(n+1)][ld_loc]; b, the labels and the state are replicated.  Per pivot:
+ *   spx_shard_candidate : local K1 — this shard's best entering column (key;
+ *                         none = all ones) and that column's n+1 cells, packed
+ *                         into d_send = [header | column], spx_shard_msg_doubles(n)
+ *                         doubles;
+ *   (all-gather of d_send over NCCL/NVLink — done by the caller)
+ *   spx_shard_select    : global K1 (min key over ranks) + K2 ratio test on the
+ *                         winning column with the replicated b; writes d_state
+ *                         (c is GLOBAL) and d_colbuf;
+ *   spx_shard_update    : K3 on the local columns; every rank updates its b.
+ * With nranks == 1 the three calls reproduce spx_pick + spx_update exactly. */
+int64_t spx_shard_msg_doubles(int32_t n);
+int spx_shard_candidate(const double *d_A, const double *d_b, int32_t n, int32_t m_loc,
+                        int64_t ld_loc, int64_t col0, int32_t rule, int32_t sticky,
+                        spx_state *d_state, double *d_send, void *stream);
+int spx_shard_select(const double *d_gathered, int32_t nranks, const double *d_b,
+                     int32_t n, int32_t rule, int32_t sticky, spx_state *d_state,
+                     double *d_colbuf, void *stream);
+int spx_shard_update(const double *d_Ain, double *d_Aout, const double *d_bin, double *d_bout,
+                     int32_t n, int32_t m_loc, int64_t ld_loc, int64_t col0,
+                     spx_state *d_state, const double *d_colbuf,
+                     int32_t *d_rowlab, int32_t *d_collab, int32_t *d_trace, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPX_B200_H */

@@ -1,0 +1,122 @@
+"""Synthetic LP generators and digest conventions for the five BASELINE.json configs.
+
+These are measurement-input specifications, not
+solver code: numpy 2.x ``default_rng`` (PCG64), fixed draw order.  Every LP is
+in the reference's input convention (``SimplexMethod(constraints, function)``,
+/root/reference/src/simplex.py:25): row i of ``constraints`` is
+``[a_i1..a_im, b_i]`` meaning ``a_i.x + b_i >= 0``, and ``function`` is
+minimised.
+"""
+from __future__ import annotations
+
+import hashlib
+import struct
+
+import numpy as np
+
+
+def dense_lp(n: int, m: int, seed: int = 0):
+    """D(n, m, seed): dense, origin-feasible, bounded (cfg2: 1000x2000, cfg4: 16384x32768).
+
+    Returns (rows [n, m+1] fp64, c [m] fp64).
+    """
+    g = np.random.default_rng(seed)
+    rows = np.empty((n, m + 1), dtype=np.float64)
+    # draw order A, b, c — written straight into the [A | b] matrix so cfg4 never
+    # holds two 4.3 GB copies
+    rows[:, :m] = g.uniform(0.1, 1.0, (n, m))
+    np.negative(rows[:, :m], out=rows[:, :m])
+    rows[:, m] = g.uniform(1.0, 2.0, n) * m
+    c = -g.uniform(0.1, 1.0, m)
+    return rows, c
+
+
+def gui_batch(B: int, seed: int = 0):
+    """P(B, seed): GUI-like 8-constraint / 2-variable LPs (cfg3: B=65536).
+
+    Bounded octagon around (5, 5), origin infeasible (exercises the phase-1
+    branch, simplex.py:72-91), coefficients rounded to 2 dp as the GUI does
+    (plot_widget.py:408).  Returns (T [B, 8, 3], C [B, 2]).
+    """
+    g = np.random.default_rng(seed)
+    k = np.arange(8)[None, :]
+    th = 2 * np.pi * (k + g.uniform(0, 1, (B, 8))) / 8
+    nx, ny = -np.cos(th), -np.sin(th)
+    r = g.uniform(1.0, 4.0, (B, 8))
+    p0 = 5.0
+    T = np.round(np.stack([nx, ny, r - (nx * p0 + ny * p0)], axis=2), 2)
+    ph = g.uniform(0, 2 * np.pi, B)
+    C = np.round(np.stack([np.cos(ph), np.sin(ph)], axis=1), 2)
+    return T, C
+
+
+def klee_minty(n: int):
+    """KM(n): Klee-Minty cube, all floats (cfg5: n=20, 2^n - 1 pivots)."""
+    rows = []
+    for i in range(1, n + 1):
+        r = [0.0] * (n + 1)
+        for j in range(1, i):
+            r[j - 1] = -float(2 ** (i - j + 1))
+        r[i - 1] = -1.0
+        r[n] = float(5 ** i)
+        rows.append(r)
+    c = [-float(2 ** (n - j)) for j in range(1, n + 1)]
+    return np.asarray(rows, dtype=np.float64), np.asarray(c, dtype=np.float64)
+
+
+# the reference's own cfg1 example, simplex.py:205-209
+CFG1_ROWS = [[-39.70, -96.00, 4060.80],
+             [-45.50, 45.30, 600.60],
+             [45.50, -7.40, -54.60],
+             [24.20, 45.10, -1091.42]]
+CFG1_C = [-1.0, -1.0]
+
+
+def batch_flat(T: np.ndarray, C: np.ndarray) -> np.ndarray:
+    """[B, n, m+1] rows + [B, m] functions -> [B, cells] reference-flat tables."""
+    B = T.shape[0]
+    return np.ascontiguousarray(np.concatenate([T.reshape(B, -1), C.reshape(B, -1)], axis=1),
+                                dtype=np.float64)
+
+
+def input_digest(rows: np.ndarray, c: np.ndarray) -> str:
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(rows).astype("<f8", copy=False).tobytes())
+    h.update(np.ascontiguousarray(c).astype("<f8", copy=False).tobytes())
+    return h.hexdigest()
+
+
+def pivot_digest(trace) -> str:
+    """sha256 over '<ii' (r, c) per pivot, in order (single LP)."""
+    t = np.ascontiguousarray(np.asarray(trace, dtype="<i4").reshape(-1, 2))
+    return hashlib.sha256(t.tobytes()).hexdigest()
+
+
+def batch_pivot_digest(trace: np.ndarray, npiv: np.ndarray) -> str:
+    """sha256 over '<iii' (k, r, c) for LP k in order, each pivot in order."""
+    B = trace.shape[0]
+    npiv = np.asarray(npiv).astype(np.int64)
+    kk = np.repeat(np.arange(B, dtype=np.int64), npiv)
+    pos = np.arange(int(npiv.sum()), dtype=np.int64) - np.repeat(np.cumsum(npiv) - npiv, npiv)
+    rc = np.asarray(trace)[kk, pos]
+    rec = np.empty((kk.shape[0], 3), dtype="<i4")
+    rec[:, 0] = kk
+    rec[:, 1:] = rc
+    return hashlib.sha256(rec.tobytes()).hexdigest()
+
+
+def batch_solution_digest(x1, x2, f) -> str:
+    """sha256 over '<ddd' (x1, x2, f) per LP."""
+    rec = np.stack([np.asarray(x1, dtype="<f8"), np.asarray(x2, dtype="<f8"),
+                    np.asarray(f, dtype="<f8")], axis=1)
+    return hashlib.sha256(np.ascontiguousarray(rec).tobytes()).hexdigest()
+
+
+def snapshot_digest(tables) -> str:
+    """sha256 over every cell of every snapshot table, '<d', row-major."""
+    h = hashlib.sha256()
+    for tab in tables:
+        for row in tab:
+            for v in row:
+                h.update(struct.pack("<d", float(v)))
+    return h.hexdigest()
