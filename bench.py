@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py — pivots/sec + tableau-update HBM GB/s on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): cfg4 of BASELINE.json — the dense 16384 x 32768 fp64 LP
+D(16384, 32768, seed 0) of SURVEY.md §8d.  One *step* = PIVOTS_PER_STEP consecutive
+pivots (pick + rank-1 update) of that tableau.  The full solve needs ~1e6 pivots, so
+timed steps simply continue the same solve; the pivot sequence of the run is checked
+against the golden prefix (tests/golden/cfg_digests.json) before anything is printed.
+
+  value   pivots/s with the tableau resident in HBM (CUDA events, max over ranks)
+  e2e     pivots/s through the public API (SimplexMethod(rows, c).solve(...)) with the
+          4.3 GB tableau in PINNED HOST memory: upload + pivots + result read-back
+  roofline  the update kernel alone: 16 B x cells per launch / its CUDA-event duration
+  cpu_baseline  oracle/spx_oracle.c (a C port of the reference's loop, OpenMP) on this host
+
+N > 1 (torchrun): the body is column-sharded, one process per GPU, one all-gather of
+{key, candidate column} per pivot over NCCL (strong scaling: the tableau is fixed).
+--impl reference: the reference's algorithm on the host cores (the oracle port; the
+reference itself is pure Python and cannot travel to the GPU box), same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ROWS, M_COLS, SEED = 16384, 32768, 0
+PIVOTS_PER_STEP = 200
+METRIC = "pivots/sec (16k x 32k fp64 tableau)"
+UNIT = "pivots/s"
+
+
+def cells(n, m):
+    return n * (m + 1) + m
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy_ burst)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def golden_trace():
+    p = os.path.join(ROOT, "tests", "golden", "cfg_digests.json")
+    with open(p) as fh:
+        g = json.load(fh)["cfg4"]
+    return g["input_sha256"], np.asarray(g["trace"], dtype=np.int32)
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs (NVML)."""
+
+    def __init__(self, index: int, period: float = 0.1):
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {
+                getattr(nv, "nvmlClocksEventReasonGpuIdle", 0x1): "gpu_idle",
+                getattr(nv, "nvmlClocksEventReasonApplicationsClocksSetting", 0x2): "applications_clocks_setting",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSyncBoost", 0x10): "sync_boost",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+            }
+            while not self._stop.is_set():
+                self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for bit, name in names.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+                self._stop.wait(self.period)
+        except Exception as e:  # NVML missing: report that instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": int(statistics.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": self.max_mhz, "samples": len(self.sm), "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's algorithm on the host cores: oracle/spx_oracle.c (C port, OpenMP)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from simplex_method_solver_b200 import workloads as W
+    oracle.build()
+    threads = oracle.num_threads()
+    per_step = max(1, args.ref_pivots_per_step)
+    log(f"[reference] generating D({N_ROWS},{M_COLS},{SEED}) ...")
+    rows, c = W.dense_lp(N_ROWS, M_COLS, SEED)
+    T = np.concatenate([rows.reshape(-1), c])
+    del rows
+    Nn = np.empty_like(T)
+    L = oracle.lib()
+    _, gold = golden_trace()
+    k = 0
+
+    def step():
+        nonlocal T, Nn, k
+        for _ in range(per_step):
+            st, r, cc, _e = oracle.pick(T, N_ROWS, M_COLS)
+            assert st == oracle.PIVOT
+            if k < len(gold):
+                assert (r, cc) == tuple(gold[k]), "oracle diverged from its own golden trace"
+            L.orc_update(oracle._dp(T), oracle._dp(Nn), N_ROWS, M_COLS, r, cc)
+            T, Nn = Nn, T
+            k += 1
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{per_step} pivots per step x {args.steps} steps of the same 16384x32768 tableau "
+                                   f"(oracle/spx_oracle.c, OpenMP {threads} threads; the reference itself is "
+                                   f"single-threaded pure Python, ~1.5e6 cells/s)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(ngpu):
+    return {"workload": "cfg4: dense LP D(n=16384, m=32768, seed=0), fp64 tableau 4.295 GB (x2 ping-pong)",
+            "n": N_ROWS, "m": M_COLS, "cells": cells(N_ROWS, M_COLS),
+            "pivots_per_step": PIVOTS_PER_STEP,
+            "parallelism": "single GPU" if ngpu == 1 else f"column-sharded x{ngpu}, one all-gather per pivot",
+            "l2_policy": "inputs (8.6 GB per pivot) far exceed the 126 MB L2; no flush needed",
+            "rule": "reference (first-negative entering, max-negative-ratio leaving)"}
+
+
+# ------------------------------------------------------------------------------ our arm
+def cpu_baseline_sample(rows, c, gold, budget_s=20.0):
+    """oracle port timed on a bounded sample of the same workload (rank 0, N=1 only)."""
+    import oracle
+    oracle.build()
+    threads = oracle.num_threads()
+    T = np.concatenate([rows.reshape(-1), c])
+    Nn = np.empty_like(T)
+    L = oracle.lib()
+    done, t_used = 0, 0.0
+    # one untimed pivot to fault the pages in
+    while True:
+        t0 = time.perf_counter()
+        st, r, cc, _e = oracle.pick(T, N_ROWS, M_COLS)
+        assert st == oracle.PIVOT and (r, cc) == tuple(gold[done])
+        L.orc_update(oracle._dp(T), oracle._dp(Nn), N_ROWS, M_COLS, r, cc)
+        T, Nn = Nn, T
+        dt = time.perf_counter() - t0
+        done += 1
+        if done > 1:
+            t_used += dt
+        if t_used > budget_s or done >= 64:
+            break
+    timed = done - 1
+    return {"value": timed / t_used, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {timed} pivots (after 1 untimed) of the same 16384x32768 tableau, "
+                      f"oracle/spx_oracle.c with OpenMP on {threads} threads"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from simplex_method_solver_b200 import _native as N
+    from simplex_method_solver_b200 import workloads as W
+    from simplex_method_solver_b200.engine import DeviceTableau
+    from simplex_method_solver_b200.simplex import SimplexMethod
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N.lib()
+    peak, peak_src = measured_peak()
+    in_sha, gold = golden_trace()
+
+    log(f"[rank {rank}] generating D({N_ROWS},{M_COLS},{SEED}) ...")
+    t0 = time.perf_counter()
+    rows, c = W.dense_lp(N_ROWS, M_COLS, SEED)
+    log(f"[rank {rank}] generated in {time.perf_counter() - t0:.1f}s")
+    P = PIVOTS_PER_STEP
+    need = (args.warmup + args.steps) * P
+
+    if world == 1:
+        # ---------------- value: tableau resident in HBM --------------------------------
+        tab = DeviceTableau(N_ROWS, M_COLS, device=dev, trace_capacity=need)
+        tab.load(rows, c, max_pivots=need)
+        for _ in range(args.warmup):
+            st, npiv = tab.solve(chunk=P, stop_after=P)
+        torch.cuda.synchronize()
+        N.load().spx_launch_count(1)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(args.steps):
+                st, npiv = tab.solve(chunk=P, stop_after=P)
+            ev1.record()
+            torch.cuda.synchronize()
+        launches = int(N.load().spx_launch_count(0))
+        total_ms = ev0.elapsed_time(ev1)
+        assert npiv == need and st == N.PIVOT, (st, npiv)
+        tr = tab.trace[:need].cpu().numpy()
+        k = min(need, len(gold))
+        assert (tr[:k] == gold[:k]).all(), "pivot sequence differs from the golden prefix"
+        value = args.steps * P / (total_ms * 1e-3)
+
+        # ---------------- roofline: the update kernel alone, CUDA events per launch -----
+        nmeas = 40
+        tab2_npiv = need
+        st_obj = tab.read_state()
+        st_obj.max_pivots = need + nmeas + 1
+        tab.write_state(st_obj)
+        tab.trace = None
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nmeas)]
+        pick_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nmeas)]
+        for q in range(nmeas):
+            pick_evs[q][0].record()
+            tab.pick(tab2_npiv, sticky=True)
+            pick_evs[q][1].record()
+            evs[q][0].record()
+            tab.update(tab2_npiv)
+            evs[q][1].record()
+            tab2_npiv += 1
+        torch.cuda.synchronize()
+        upd_ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        pick_ms = statistics.mean(a.elapsed_time(b) for a, b in pick_evs)
+        alg_bytes = 16.0 * cells(N_ROWS, M_COLS)
+        achieved = alg_bytes / (upd_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "update_kernel_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": "update_kernel (K3 rank-1 update)", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
+                    "update_ms": upd_ms, "pick_ms": pick_ms,
+                    "update_share_of_step": upd_ms * P / (total_ms / args.steps),
+                    "frac_of_nominal_8TBs": achieved / 8000.0}
+        del tab
+        torch.cuda.empty_cache()
+
+        # ---------------- e2e: public API, pinned host input, upload inside the timed region
+        pinned = torch.empty((N_ROWS, M_COLS + 1), dtype=torch.float64).pin_memory()
+        pinned.numpy()[...] = rows
+        host_rows = pinned.numpy()
+        h2d = host_rows.nbytes + c.nbytes
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_t, d2h = [], 0
+        for it in range(1 + e2e_steps):            # first iteration is a warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sm = SimplexMethod(host_rows, c, device=dev, engine="stream")
+            sol = sm.solve(max_pivots=P, chunk=P)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            assert sol.npiv == P and (sol.trace == gold[:P]).all()
+            d2h = sol.trace.nbytes + sol.x.nbytes + 16 + sol.rowlab.nbytes + sol.collab.nbytes
+            if it > 0:
+                e2e_t.append(dt)
+            del sm
+        e2e_val = P / statistics.mean(e2e_t)
+
+        cpu = cpu_baseline_sample(rows, c, gold) if not args.no_cpu_baseline else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(1), "clocks": clk.summary(),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * statistics.mean(e2e_t),
+                    "api": "SimplexMethod(pinned_rows, c).solve(max_pivots=200)"},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "hbm_gbs_whole_step": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9,
+            "parity": f"pivot sequence == golden prefix for the first {k} pivots",
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------- N > 1: column-sharded, one process per GPU ---------------------------
+    from simplex_method_solver_b200.parallel import ShardedTableau
+    sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need)
+    sh.load(rows, c, max_pivots=need)
+    del rows
+    for _ in range(args.warmup):
+        sh.run(P)
+    torch.cuda.synchronize()
+    dist.barrier()
+    N.load().spx_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            sh.run(P)
+        ev1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+    launches = int(N.load().spx_launch_count(0))
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    st = sh.read_state()
+    assert st.npiv == need and st.status == N.PIVOT, (st.status, st.npiv)
+    tr = sh.trace[:need].cpu().numpy()
+    k = min(need, len(gold))
+    assert (tr[:k] == gold[:k]).all(), "sharded pivot sequence differs from the golden prefix"
+    value = args.steps * P / (total_ms * 1e-3)
+    alg_bytes = 16.0 * cells(N_ROWS, M_COLS)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(world), "clocks": clk.summary(),
+            "e2e": None, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "update_kernel (K3), whole step incl. exchange",
+                         "achieved": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9 / world,
+                         "peak": peak, "unit": "GB/s per GPU", "peak_source": peak_src,
+                         "frac": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9 / world / peak,
+                         "traffic": None},
+            "cpu_baseline": None,
+            "parity": f"sharded pivot sequence == golden prefix for the first {k} pivots",
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-pivots-per-step", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("note: the timing rules ask for >= 3 warm-up steps")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,18 +90,21 @@ int         spx_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_mi
 int64_t     spx_launch_count(int reset);
 
 /* ---- layout conversion (SimplexMethod.__init__, simplex.py:25-39) -------- */
-/* src is reference-flat, host or device (cudaMemcpyDefault); dst is split; the
- * padding columns of d_A are zeroed. */
-int spx_import_table(const double *src_flat, double *d_A, double *d_b,
+/* src_rows is the reference's `constraints` as a dense row-major [n][m+1] fp64
+ * array, src_function its `function` [m]; both host or device
+ * (cudaMemcpyDefault).  For a reference-flat buffer pass
+ * src_function = src_rows + n*(m+1).  dst is split; the padding columns of d_A
+ * are zeroed.  Host sources should be pinned for full PCIe bandwidth. */
+int spx_import_table(const double *src_rows, const double *src_function, double *d_A, double *d_b,
                      int32_t n, int32_t m, int64_t ld, void *stream);
-/* Column block [col0, col0+m_loc) of a reference-flat table -> a local split
- * body d_A[(n+1)][ld_loc] (+ b when d_b != NULL): the loader of one column shard. */
-int spx_import_shard(const double *src_flat, double *d_A, double *d_b,
+/* Column block [col0, col0+m_loc) of the same source -> a local split body
+ * d_A[(n+1)][ld_loc] (+ b when d_b != NULL): the loader of one column shard. */
+int spx_import_shard(const double *src_rows, const double *src_function, double *d_A, double *d_b,
                      int32_t n, int32_t m, int64_t col0, int32_t m_loc, int64_t ld_loc,
                      void *stream);
-/* split -> reference-flat (host or device destination): what Info.table /
- * SimplexMethod.table expose (simplex.py:16,36-39). */
-int spx_export_table(const double *d_A, const double *d_b, double *dst_flat,
+/* split -> [n][m+1] rows + [m] f row (host or device destinations): what
+ * Info.table / SimplexMethod.table expose (simplex.py:16,36-39). */
+int spx_export_table(const double *d_A, const double *d_b, double *dst_rows, double *dst_function,
                      int32_t n, int32_t m, int64_t ld, void *stream);
 /* state = {running, npiv 0, cap}, labels x1..xm / y1..yn (simplex.py:30-33) */
 int spx_init_state(spx_state *d_state, int32_t *d_rowlab, int32_t *d_collab,

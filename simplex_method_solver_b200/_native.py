@@ -1,0 +1,124 @@
+"""ctypes binding of libspx_b200.so (C ABI declared in include/spx_b200.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is
+usable, every product entry point raises ``NativeUnavailable`` loudly.
+PyTorch is used by the callers only to allocate device memory and to obtain
+stream handles; nothing here takes or returns a torch type.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libspx_b200.so")
+
+PIVOT, OPTIMAL, INCORRECT, NOCONV, CAP = 1, 0, -1, -2, -3
+RULE_REFERENCE, RULE_DANTZIG = 0, 1
+RULES = {"reference": RULE_REFERENCE, "bland": RULE_REFERENCE, "dantzig": RULE_DANTZIG}
+
+# the two ValueError texts of pick_element(), /root/reference/src/simplex.py:89,139
+ERROR_TEXT = {INCORRECT: "incorrect system", NOCONV: "simplex method does not converge"}
+
+
+class NativeUnavailable(RuntimeError):
+    pass
+
+
+class SpxError(RuntimeError):
+    pass
+
+
+class SpxState(ctypes.Structure):
+    """Mirror of ``spx_state`` (include/spx_b200.h), 128 bytes."""
+    _fields_ = [
+        ("status", ctypes.c_int32), ("r", ctypes.c_int32),
+        ("c", ctypes.c_int64), ("p", ctypes.c_double),
+        ("npiv", ctypes.c_int64), ("max_pivots", ctypes.c_int64),
+        ("phase1", ctypes.c_int32), ("slot", ctypes.c_int32),
+        ("hint_tag", ctypes.c_int64 * 2),
+        ("hint_bneg", ctypes.c_int32 * 2), ("hint_fneg", ctypes.c_int32 * 2),
+        ("reserved", ctypes.c_int64 * 6),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/spx_b200.h declares
+_vp, _i32, _i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+_pi32, _pi64 = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64)
+SIGNATURES = {
+    "spx_version": (ctypes.c_int, []),
+    "spx_last_error": (ctypes.c_char_p, []),
+    "spx_ld": (_i64, [_i64]),
+    "spx_cells": (_i64, [_i32, _i32]),
+    "spx_colbuf_doubles": (_i64, [_i32]),
+    "spx_state_bytes": (ctypes.c_int, []),
+    "spx_device_info": (ctypes.c_int, [_pi32, _pi32, _pi32]),
+    "spx_launch_count": (_i64, [ctypes.c_int]),
+    "spx_import_table": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp]),
+    "spx_import_shard": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i64, _vp]),
+    "spx_export_table": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp]),
+    "spx_init_state": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp]),
+    "spx_pick": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "spx_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spx_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
+                                 _i32, _i64, _pi32, _pi64, _vp]),
+    "spx_extract": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "spx_solve_batched": (ctypes.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         _vp, _vp, _vp]),
+    "spx_batched_max_cells": (_i64, []),
+    "spx_shard_msg_doubles": (_i64, [_i32]),
+    "spx_shard_candidate": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "spx_shard_select": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "spx_shard_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp,
+                                        _vp, _vp]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the library and bind every declared symbol (no GPU needed for this)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeUnavailable(
+            f"{LIB_PATH} is missing: build it with `python -m simplex_method_solver_b200.build` "
+            "(there is no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)           # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if L.spx_version() != 1:
+        raise NativeUnavailable("libspx_b200.so ABI version mismatch")
+    if L.spx_state_bytes() != ctypes.sizeof(SpxState):
+        raise NativeUnavailable("spx_state layout mismatch between header and Python mirror")
+    _lib = L
+    return L
+
+
+def lib() -> ctypes.CDLL:
+    """The library, for compute calls: also requires a CUDA device."""
+    import torch
+    L = load()
+    if not torch.cuda.is_available():
+        raise NativeUnavailable("no CUDA device: the B200 pivot kernels cannot run (there is no CPU fallback)")
+    return L
+
+
+def call(name: str, *args) -> None:
+    L = lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise SpxError(f"{name} failed ({rc}): {L.spx_last_error().decode(errors='replace')}")
+
+
+def ptr(t) -> int:
+    """Device/host pointer of a torch tensor (or None)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_handle() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

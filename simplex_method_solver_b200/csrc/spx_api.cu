@@ -1,0 +1,294 @@
+// spx_api.cu — the extern "C" boundary of libspx_b200.so (see include/spx_b200.h).
+// Plain pointers and sizes only; no torch types.  Every entry validates its
+// arguments, launches on the caller's stream and reports failures through
+// spx_last_error().
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "spx_common.cuh"
+
+namespace spx_launch {
+int     sm_count();
+int64_t colbuf_doubles(int n);
+int64_t shard_msg_doubles(int n);
+int64_t batched_max_cells();
+cudaError_t pick(const double *, const double *, int, int, int64_t, int, int, spx_state *, double *,
+                 cudaStream_t);
+cudaError_t shard_candidate(const double *, const double *, int, int, int64_t, int64_t, int, int,
+                            const spx_state *, double *, cudaStream_t);
+cudaError_t shard_select(const double *, int, const double *, int, int, spx_state *, double *,
+                         cudaStream_t);
+cudaError_t update(const double *, double *, const double *, double *, int, int, int64_t, int64_t,
+                   spx_state *, const double *, int32_t *, int32_t *, int32_t *, cudaStream_t);
+cudaError_t extract(const double *, int, int, const int32_t *, const double *, double *, double *,
+                    cudaStream_t);
+cudaError_t init_state(spx_state *, int32_t *, int32_t *, int, int, int64_t, cudaStream_t);
+cudaError_t solve_batched(double *, int64_t, int, int, int, int, double *, double *, int32_t *,
+                          int32_t *, int32_t *, int32_t *, int32_t *, double *, cudaStream_t);
+} // namespace spx_launch
+
+namespace spx_host {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return 0;
+    set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return -1;
+}
+
+void count_launch(int k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+
+} // namespace spx_host
+
+using spx_host::check;
+using spx_host::set_error;
+
+#define SPX_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            set_error(__VA_ARGS__);       \
+            return -2;                    \
+        }                                 \
+    } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int spx_version(void) { return SPX_ABI_VERSION; }
+
+const char *spx_last_error(void) { return spx_host::g_err; }
+
+int64_t spx_ld(int64_t m) {
+    int64_t ld = (m + 15) / 16 * 16;
+    return ld < 16 ? 16 : ld;
+}
+
+int64_t spx_cells(int32_t n, int32_t m) { return (int64_t)n * (m + 1) + m; }
+
+int64_t spx_colbuf_doubles(int32_t n) { return spx_launch::colbuf_doubles(n); }
+
+int spx_state_bytes(void) { return (int)sizeof(spx_state); }
+
+int spx_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor) {
+    int dev = 0;
+    if (check(cudaGetDevice(&dev), "cudaGetDevice")) return -1;
+    int sms = 0, maj = 0, min = 0;
+    if (check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "attr")) return -1;
+    if (check(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev), "attr")) return -1;
+    if (check(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev), "attr")) return -1;
+    if (sm_count) *sm_count = sms;
+    if (cc_major) *cc_major = maj;
+    if (cc_minor) *cc_minor = min;
+    return 0;
+}
+
+int64_t spx_launch_count(int reset) {
+    long long v = spx_host::g_launches.load(std::memory_order_relaxed);
+    if (reset) spx_host::g_launches.store(0, std::memory_order_relaxed);
+    return v;
+}
+
+// ---- layout conversion ---------------------------------------------------------
+int spx_import_shard(const double *src_rows, const double *src_function, double *d_A, double *d_b,
+                     int32_t n, int32_t m, int64_t col0, int32_t m_loc, int64_t ld_loc, void *stream) {
+    SPX_REQUIRE(src_rows && src_function && d_A, "spx_import_shard: null pointer");
+    SPX_REQUIRE(n >= 0 && m >= 1 && m_loc >= 0 && col0 >= 0 && col0 + m_loc <= m,
+                "spx_import_shard: bad shape n=%d m=%d col0=%lld m_loc=%d", n, m, (long long)col0, m_loc);
+    SPX_REQUIRE(ld_loc >= m_loc && ld_loc % 16 == 0, "spx_import_shard: ld=%lld must be a multiple of 16 >= m_loc",
+                (long long)ld_loc);
+    cudaStream_t s = as_stream(stream);
+    const size_t spitch = (size_t)(m + 1) * sizeof(double);
+    const size_t dpitch = (size_t)ld_loc * sizeof(double);
+    if (m_loc > 0 && n > 0)
+        if (check(cudaMemcpy2DAsync(d_A, dpitch, src_rows + col0, spitch, (size_t)m_loc * sizeof(double),
+                                    (size_t)n, cudaMemcpyDefault, s), "import body")) return -1;
+    if (m_loc > 0)   // the f row has m cells (simplex.py:39)
+        if (check(cudaMemcpyAsync(d_A + (size_t)n * ld_loc, src_function + col0,
+                                  (size_t)m_loc * sizeof(double), cudaMemcpyDefault, s), "import f row")) return -1;
+    if (ld_loc > m_loc)
+        if (check(cudaMemset2DAsync(d_A + m_loc, dpitch, 0, (size_t)(ld_loc - m_loc) * sizeof(double),
+                                    (size_t)n + 1, s), "zero padding")) return -1;
+    if (d_b && n > 0)
+        if (check(cudaMemcpy2DAsync(d_b, sizeof(double), src_rows + m, spitch, sizeof(double), (size_t)n,
+                                    cudaMemcpyDefault, s), "import b")) return -1;
+    return 0;
+}
+
+int spx_import_table(const double *src_rows, const double *src_function, double *d_A, double *d_b,
+                     int32_t n, int32_t m, int64_t ld, void *stream) {
+    SPX_REQUIRE(d_b, "spx_import_table: null d_b");
+    return spx_import_shard(src_rows, src_function, d_A, d_b, n, m, 0, m, ld, stream);
+}
+
+int spx_export_table(const double *d_A, const double *d_b, double *dst_rows, double *dst_function,
+                     int32_t n, int32_t m, int64_t ld, void *stream) {
+    SPX_REQUIRE(d_A && d_b && dst_rows && dst_function, "spx_export_table: null pointer");
+    SPX_REQUIRE(n >= 0 && m >= 1 && ld >= m, "spx_export_table: bad shape");
+    cudaStream_t s = as_stream(stream);
+    const size_t dpitch = (size_t)(m + 1) * sizeof(double);
+    const size_t spitch = (size_t)ld * sizeof(double);
+    if (n > 0) {
+        if (check(cudaMemcpy2DAsync(dst_rows, dpitch, d_A, spitch, (size_t)m * sizeof(double), (size_t)n,
+                                    cudaMemcpyDefault, s), "export body")) return -1;
+        if (check(cudaMemcpy2DAsync(dst_rows + m, dpitch, d_b, sizeof(double), sizeof(double), (size_t)n,
+                                    cudaMemcpyDefault, s), "export b")) return -1;
+    }
+    if (check(cudaMemcpyAsync(dst_function, d_A + (size_t)n * ld,
+                              (size_t)m * sizeof(double), cudaMemcpyDefault, s), "export f row")) return -1;
+    return 0;
+}
+
+int spx_init_state(spx_state *d_state, int32_t *d_rowlab, int32_t *d_collab, int32_t n, int32_t m,
+                   int64_t max_pivots, void *stream) {
+    SPX_REQUIRE(d_state && d_rowlab && d_collab, "spx_init_state: null pointer");
+    SPX_REQUIRE(n >= 0 && m >= 1 && max_pivots >= 0, "spx_init_state: bad arguments");
+    return check(spx_launch::init_state(d_state, d_rowlab, d_collab, n, m, max_pivots, as_stream(stream)),
+                 "init_state launch");
+}
+
+// ---- K1 + K2 ------------------------------------------------------------------
+static int validate_split(const char *who, const void *A, const void *b, int n, int m, int64_t ld) {
+    SPX_REQUIRE(A && b, "%s: null tableau pointer", who);
+    SPX_REQUIRE(n >= 1 && m >= 0, "%s: bad shape n=%d m=%d", who, n, m);
+    SPX_REQUIRE(ld >= m && ld >= 16 && ld % 16 == 0, "%s: ld=%lld must be a multiple of 16 >= m", who, (long long)ld);
+    SPX_REQUIRE(((uintptr_t)A & 127) == 0, "%s: tableau body must be 128-byte aligned", who);
+    return 0;
+}
+
+int spx_pick(const double *d_A, const double *d_b, int32_t n, int32_t m, int64_t ld, int32_t rule,
+             int32_t sticky, spx_state *d_state, double *d_colbuf, void *stream) {
+    if (validate_split("spx_pick", d_A, d_b, n, m, ld)) return -2;
+    SPX_REQUIRE(d_state && d_colbuf, "spx_pick: null state/colbuf");
+    SPX_REQUIRE(rule == SPX_RULE_REFERENCE || rule == SPX_RULE_DANTZIG, "spx_pick: unknown rule %d", rule);
+    return check(spx_launch::pick(d_A, d_b, n, m, ld, rule, sticky, d_state, d_colbuf, as_stream(stream)),
+                 "pick launch");
+}
+
+// ---- K3 -----------------------------------------------------------------------
+int spx_shard_update(const double *d_Ain, double *d_Aout, const double *d_bin, double *d_bout,
+                     int32_t n, int32_t m_loc, int64_t ld_loc, int64_t col0, spx_state *d_state,
+                     const double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab, int32_t *d_trace,
+                     void *stream) {
+    if (validate_split("spx_update", d_Ain, d_bin, n, m_loc, ld_loc)) return -2;
+    if (validate_split("spx_update", d_Aout, d_bout, n, m_loc, ld_loc)) return -2;
+    SPX_REQUIRE(d_Ain != d_Aout && d_bin != d_bout, "spx_update: the pivot is out of place; in == out");
+    SPX_REQUIRE(d_state && d_colbuf && d_rowlab && d_collab, "spx_update: null state/colbuf/labels");
+    SPX_REQUIRE(((uintptr_t)d_colbuf & 15) == 0, "spx_update: colbuf must be 16-byte aligned");
+    return check(spx_launch::update(d_Ain, d_Aout, d_bin, d_bout, n, m_loc, ld_loc, col0, d_state, d_colbuf,
+                                    d_rowlab, d_collab, d_trace, as_stream(stream)), "update launch");
+}
+
+int spx_update(const double *d_Ain, double *d_Aout, const double *d_bin, double *d_bout, int32_t n,
+               int32_t m, int64_t ld, spx_state *d_state, const double *d_colbuf, int32_t *d_rowlab,
+               int32_t *d_collab, int32_t *d_trace, void *stream) {
+    return spx_shard_update(d_Ain, d_Aout, d_bin, d_bout, n, m, ld, 0, d_state, d_colbuf, d_rowlab,
+                            d_collab, d_trace, stream);
+}
+
+// ---- the pivot loop -------------------------------------------------------------
+int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n, int32_t m, int64_t ld,
+              int32_t rule, spx_state *d_state, double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab,
+              int32_t *d_trace, int32_t chunk, int64_t stop_after, int32_t *h_status, int64_t *h_npiv,
+              void *stream) {
+    if (validate_split("spx_solve", d_A0, d_b0, n, m, ld)) return -2;
+    if (validate_split("spx_solve", d_A1, d_b1, n, m, ld)) return -2;
+    SPX_REQUIRE(d_state && d_colbuf && d_rowlab && d_collab, "spx_solve: null state/colbuf/labels");
+    SPX_REQUIRE(chunk >= 1, "spx_solve: chunk must be >= 1");
+    SPX_REQUIRE(rule == SPX_RULE_REFERENCE || rule == SPX_RULE_DANTZIG, "spx_solve: unknown rule %d", rule);
+    cudaStream_t s = as_stream(stream);
+    double *A[2] = {d_A0, d_A1};
+    double *b[2] = {d_b0, d_b1};
+    spx_state hs;
+    if (check(cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, s), "read state")) return -1;
+    if (check(cudaStreamSynchronize(s), "sync")) return -1;
+    if (hs.status == SPX_CAP && hs.npiv < hs.max_pivots) {   // the caller raised the cap: resume
+        const int32_t run = SPX_PIVOT;
+        if (check(cudaMemcpyAsync(&d_state->status, &run, sizeof(run), cudaMemcpyHostToDevice, s), "resume")) return -1;
+        hs.status = SPX_PIVOT;
+    }
+    int64_t done = 0;
+    while (hs.status == SPX_PIVOT) {
+        int64_t k = chunk;
+        if (stop_after > 0 && stop_after - done < k) k = stop_after - done;
+        if (k <= 0) break;
+        const int64_t base = hs.npiv;
+        for (int64_t q = 0; q < k; ++q) {
+            const int cur = (int)((base + q) & 1);
+            if (check(spx_launch::pick(A[cur], b[cur], n, m, ld, rule, 1, d_state, d_colbuf, s), "pick launch")) return -1;
+            if (check(spx_launch::update(A[cur], A[cur ^ 1], b[cur], b[cur ^ 1], n, m, ld, 0, d_state, d_colbuf,
+                                         d_rowlab, d_collab, d_trace, s), "update launch")) return -1;
+        }
+        if (check(cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, s), "read state")) return -1;
+        if (check(cudaStreamSynchronize(s), "pivot chunk")) return -1;
+        done += k;
+        if (hs.status != SPX_PIVOT) break;
+    }
+    if (hs.status == SPX_PIVOT && !(stop_after > 0 && done >= stop_after)) {
+        // nothing enqueued (e.g. stop_after exhausted before the first chunk)
+    }
+    if (h_status) *h_status = hs.status;
+    if (h_npiv) *h_npiv = hs.npiv;
+    return 0;
+}
+
+// ---- find_optimum / f -----------------------------------------------------------
+int spx_extract(const double *d_b, int32_t n, int32_t m, const int32_t *d_collab,
+                const double *d_function, double *d_x, double *d_obj, void *stream) {
+    SPX_REQUIRE(d_b && d_collab && d_function && d_x && d_obj, "spx_extract: null pointer");
+    SPX_REQUIRE(n >= 1 && m >= 1, "spx_extract: bad shape");
+    return check(spx_launch::extract(d_b, n, m, d_collab, d_function, d_x, d_obj, as_stream(stream)),
+                 "extract launch");
+}
+
+// ---- K4 -------------------------------------------------------------------------
+int64_t spx_batched_max_cells(void) { return spx_launch::batched_max_cells(); }
+
+int spx_solve_batched(double *d_T, int64_t B, int32_t n, int32_t m, int32_t rule, int32_t max_pivots,
+                      double *d_x, double *d_obj, int32_t *d_status, int32_t *d_npiv, int32_t *d_rowlab,
+                      int32_t *d_collab, int32_t *d_trace, double *d_snap, void *stream) {
+    SPX_REQUIRE(B >= 0 && n >= 1 && m >= 1 && max_pivots >= 0, "spx_solve_batched: bad arguments");
+    SPX_REQUIRE(B == 0 || (d_T && d_status && d_npiv), "spx_solve_batched: null T/status/npiv");
+    SPX_REQUIRE(rule == SPX_RULE_REFERENCE || rule == SPX_RULE_DANTZIG, "spx_solve_batched: unknown rule %d", rule);
+    SPX_REQUIRE(spx_cells(n, m) <= spx_batched_max_cells(),
+                "spx_solve_batched: %lld cells per LP exceed the shared-memory resident limit %lld; use spx_solve",
+                (long long)spx_cells(n, m), (long long)spx_batched_max_cells());
+    cudaError_t e = spx_launch::solve_batched(d_T, B, n, m, rule, max_pivots, d_x, d_obj, d_status, d_npiv,
+                                              d_rowlab, d_collab, d_trace, d_snap, as_stream(stream));
+    return check(e, "batched launch");
+}
+
+// ---- column-sharded flow ----------------------------------------------------------
+int64_t spx_shard_msg_doubles(int32_t n) { return spx_launch::shard_msg_doubles(n); }
+
+int spx_shard_candidate(const double *d_A, const double *d_b, int32_t n, int32_t m_loc, int64_t ld_loc,
+                        int64_t col0, int32_t rule, int32_t sticky, spx_state *d_state, double *d_send,
+                        void *stream) {
+    if (validate_split("spx_shard_candidate", d_A, d_b, n, m_loc, ld_loc)) return -2;
+    SPX_REQUIRE(d_state && d_send && col0 >= 0, "spx_shard_candidate: bad arguments");
+    SPX_REQUIRE(rule == SPX_RULE_REFERENCE || rule == SPX_RULE_DANTZIG, "spx_shard_candidate: unknown rule %d", rule);
+    return check(spx_launch::shard_candidate(d_A, d_b, n, m_loc, ld_loc, col0, rule, sticky, d_state, d_send,
+                                             as_stream(stream)), "candidate launch");
+}
+
+int spx_shard_select(const double *d_gathered, int32_t nranks, const double *d_b, int32_t n, int32_t rule,
+                     int32_t sticky, spx_state *d_state, double *d_colbuf, void *stream) {
+    (void)rule;
+    SPX_REQUIRE(d_gathered && d_b && d_state && d_colbuf && nranks >= 1 && n >= 1,
+                "spx_shard_select: bad arguments");
+    return check(spx_launch::shard_select(d_gathered, nranks, d_b, n, sticky, d_state, d_colbuf,
+                                          as_stream(stream)), "select launch");
+}
+
+} // extern "C"

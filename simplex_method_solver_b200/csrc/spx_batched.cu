@@ -1,0 +1,221 @@
+// spx_batched.cu — K4: whole-LP solver for batches of independent small LPs,
+// one warp per LP, no communication: the loop of get_solution(),
+// /root/reference/src/simplex.py:179-199, with pick_element() (:70-141) and
+// recalculate_matrix() (:143-177) inlined.
+//
+// The tableau of an LP lives in shared memory in the reference's own flat
+// layout (n rows of m+1 cells, then the f row with m cells) as two ping-pong
+// copies, because the reference pivots out of place (:149) and every cell of the
+// new table reads the OLD pivot row and column.  Lanes stride over the cells;
+// every decision is a warp ballot / shuffle reduction, so all 32 lanes always
+// take the same branch and no block-level barrier is needed after the prologue.
+// cfg1 (14 cells), cfg3 (26 cells) and Klee-Minty n=20 (440 cells, 2^20-1
+// strictly sequential pivots) all run through this kernel.
+#include "spx_common.cuh"
+
+namespace {
+
+using namespace spx;
+
+struct BatchedArgs {
+    double  *T;          // [B][cells] in/out
+    int64_t  B;
+    int      n, m, rule, max_pivots;
+    double  *x;          // [B][m] or null
+    double  *obj;        // [B] or null
+    int32_t *status;     // [B]
+    int32_t *npiv;       // [B]
+    int32_t *rowlab;     // [B][m] or null
+    int32_t *collab;     // [B][n] or null
+    int32_t *trace;      // [B][max_pivots][2] or null
+    double  *snap;       // [B][max_pivots+1][cells] or null
+};
+
+// first index q in [0, len) with pred(q); warp-uniform result
+template <class F>
+__device__ __forceinline__ int warp_first_index(int len, int lane, F pred) {
+    for (int base = 0; base < len; base += 32) {
+        const int q = base + lane;
+        const unsigned ball = __ballot_sync(0xffffffffu, q < len && pred(q));
+        if (ball) return base + __ffs(ball) - 1;
+    }
+    return SPX_NONE;
+}
+
+__global__ void __launch_bounds__(256)
+batched_kernel(BatchedArgs a, int warps_per_cta, int warp_doubles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n, m = a.m, w1 = m + 1;
+    const int cells = n * w1 + m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // CTA-shared lookup: cell -> (row, col), built once (shape is uniform over the batch)
+    uint16_t *cell_i = reinterpret_cast<uint16_t *>(smem_raw);
+    uint16_t *cell_j = cell_i + cells;
+    for (int k = threadIdx.x; k < cells; k += blockDim.x) {
+        const int i = k / w1;
+        cell_i[k] = (uint16_t)i;
+        cell_j[k] = (uint16_t)(k - i * w1);
+    }
+    __syncthreads();
+
+    const int64_t lp = (int64_t)blockIdx.x * warps_per_cta + warp;
+    if (warp >= warps_per_cta || lp >= a.B) return;
+
+    const size_t lut_bytes = ((size_t)cells * 4 + 15) / 16 * 16;
+    double *base = reinterpret_cast<double *>(smem_raw + lut_bytes) + (size_t)warp * warp_doubles;
+    double *cur = base;
+    double *nxt = base + cells;
+    double *xs  = base + 2 * cells;                       // [m]
+    int32_t *rl = reinterpret_cast<int32_t *>(xs + m);    // [m] header labels
+    int32_t *cl = rl + m;                                 // [n] row labels
+
+    double *Tg = a.T + lp * (int64_t)cells;
+    for (int k = lane; k < cells; k += 32) cur[k] = Tg[k];
+    for (int j = lane; j < m; j += 32) rl[j] = j;         // 'x1'..'xm'  :30
+    for (int i = lane; i < n; i += 32) cl[i] = m + i;     // 'y1'..'yn'  :31
+    __syncwarp();
+    const int fo = n * w1;                                // offset of the f row
+    const double f0 = (m >= 1) ? cur[fo] : 0.0;           // self.function is never mutated (:29,:49)
+    const double f1 = (m >= 2) ? cur[fo + 1] : 0.0;
+
+    int npiv = 0, status;
+    double *snap = a.snap ? a.snap + lp * (int64_t)(a.max_pivots + 1) * cells : nullptr;
+    int32_t *trace = a.trace ? a.trace + lp * (int64_t)a.max_pivots * 2 : nullptr;
+
+    for (;;) {
+        if (snap) {
+            double *sg = snap + (int64_t)npiv * cells;
+            for (int k = lane; k < cells; k += 32) sg[k] = cur[k];
+        }
+        int r, c;
+        // ---- K1: phase-1 row (:72-76), its first positive cell (:81-85) ...
+        const int r1 = warp_first_index(n, lane, [&](int i) { return cur[i * w1 + m] < 0.0; });
+        if (r1 != SPX_NONE) {
+            c = warp_first_index(m, lane, [&](int j) { return cur[r1 * w1 + j] > 0.0; });
+            if (c == SPX_NONE) { status = SPX_INCORRECT; break; }                 // :88-89
+            r = r1;                                                               // :91
+        } else {
+            // ---- ... or the entering column from the f row (:94-98)
+            if (a.rule == SPX_RULE_REFERENCE) {
+                c = warp_first_index(m, lane, [&](int j) { return cur[fo + j] < 0.0; });
+            } else {   // Dantzig: most negative, lowest index on ties
+                unsigned long long best = ~0ull;
+                for (int j = lane; j < m; j += 32) {
+                    const double v = cur[fo + j];
+                    if (v < 0.0) { const unsigned long long k = orderable(v); best = k < best ? k : best; }
+                }
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, s);
+                    best = o < best ? o : best;
+                }
+                c = (best == ~0ull) ? SPX_NONE
+                    : warp_first_index(m, lane, [&](int j) {
+                          const double v = cur[fo + j];
+                          return v < 0.0 && orderable(v) == best; });
+            }
+            if (c == SPX_NONE) { status = SPX_OPTIMAL; break; }                   // :101-103
+            // ---- K2: the ratio scan (:107-136) as a warp reduction
+            Ratio q = ratio_identity();
+            for (int i = lane; i < n; i += 32) ratio_accumulate(q, i, cur[i * w1 + c], cur[i * w1 + m]);
+            q = warp_ratio_reduce(q);
+            bool elig_nan = false;
+            if (q.elig_row != SPX_NONE) {
+                const double v = __ddiv_rn(cur[q.elig_row * w1 + m], cur[q.elig_row * w1 + c]);
+                elig_nan = (v != v);
+            }
+            r = ratio_decide(q, elig_nan);
+            if (r < 0) { status = SPX_NOCONV; break; }                            // :138-139
+        }
+        if (npiv >= a.max_pivots) { status = SPX_CAP; break; }
+        if (trace && lane == 0) { trace[2 * npiv] = r; trace[2 * npiv + 1] = c; }
+
+        // ---- K3: out-of-place pivot (:149-177), all reads from `cur`
+        const double p = cur[r * w1 + c];
+        const double *prow = cur + r * w1;
+        for (int k = lane; k < cells; k += 32) {
+            const int i = cell_i[k], j = cell_j[k];
+            const double t = cur[k];
+            double o;
+            if (i == r) {
+                o = (j == c) ? pivot_cell_update(p) : pivot_row_update(t, p);     // :163, :156
+            } else {
+                const double ci = cur[i * w1 + c];
+                o = (j == c) ? pivot_col_update(ci, p) : cell_update(t, p, prow[j], ci);   // :160, :173-175
+            }
+            nxt[k] = o;
+        }
+        if (lane == 0) { const int32_t t = rl[c]; rl[c] = cl[r]; cl[r] = t; }     // :152
+        __syncwarp();
+        double *sw = cur; cur = nxt; nxt = sw;
+        ++npiv;
+    }
+
+    // ---- epilogue: final table, labels, find_optimum()/f() (:48-68)
+    for (int k = lane; k < cells; k += 32) Tg[k] = cur[k];
+    for (int j = lane; j < m; j += 32) xs[j] = 0.0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        const int lab = cl[i];
+        if (lab < m) xs[lab] = cur[i * w1 + m];
+    }
+    __syncwarp();
+    if (a.x) for (int j = lane; j < m; j += 32) a.x[lp * m + j] = xs[j];
+    if (a.rowlab) for (int j = lane; j < m; j += 32) a.rowlab[lp * m + j] = rl[j];
+    if (a.collab) for (int i = lane; i < n; i += 32) a.collab[lp * n + i] = cl[i];
+    if (lane == 0) {
+        a.status[lp] = status;
+        a.npiv[lp] = npiv;
+        if (a.obj) a.obj[lp] = (m >= 2) ? __dadd_rn(__dmul_rn(f0, xs[0]), __dmul_rn(f1, xs[1])) : 0.0;
+    }
+}
+
+size_t warp_bytes(int n, int m) {
+    const size_t cells = (size_t)n * (m + 1) + m;
+    size_t b = (2 * cells + m) * sizeof(double) + (size_t)(n + m) * sizeof(int32_t);
+    return (b + 15) / 16 * 16;
+}
+size_t lut_bytes(int n, int m) {
+    const size_t cells = (size_t)n * (m + 1) + m;
+    return (cells * 4 + 15) / 16 * 16;
+}
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+} // namespace
+
+namespace spx_launch {
+
+int64_t batched_max_cells() { return 10000; }
+
+// returns cudaErrorInvalidValue when one LP does not fit shared memory
+cudaError_t solve_batched(double *T, int64_t B, int n, int m, int rule, int max_pivots, double *x,
+                          double *obj, int32_t *status, int32_t *npiv, int32_t *rowlab,
+                          int32_t *collab, int32_t *trace, double *snap, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    if (n > 65535 || m > 65534) return cudaErrorInvalidValue;
+    const size_t wb = warp_bytes(n, m), lb = lut_bytes(n, m);
+    if (lb + wb > SMEM_LIMIT) return cudaErrorInvalidValue;
+    // warps per CTA: as many as fit ~48 KB (several CTAs per SM), at most 8, at least 1
+    int wpc = (int)((48 * 1024 - lb) / wb);
+    if (lb >= 48 * 1024) wpc = 0;
+    wpc = wpc > 8 ? 8 : wpc;
+    if (wpc < 1) wpc = 1;
+    if ((int64_t)wpc > B) wpc = (int)B;
+    const size_t smem = lb + (size_t)wpc * wb;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(batched_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)SMEM_LIMIT);
+        if (e != cudaSuccess) return e;
+        configured = SMEM_LIMIT;
+    }
+    BatchedArgs a{T, B, n, m, rule, max_pivots, x, obj, status, npiv, rowlab, collab, trace, snap};
+    const int64_t ctas = (B + wpc - 1) / wpc;
+    batched_kernel<<<(unsigned)ctas, wpc * 32, smem, stream>>>(a, wpc, (int)(wb / sizeof(double)));
+    spx_host::count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace spx_launch

@@ -1,0 +1,282 @@
+// spx_pick.cu — K1 (pricing) + K2 (ratio test): pick_element(), /root/reference/src/simplex.py:70-141.
+//
+// One CTA of 1024 threads per pick: every decision of the reference is a
+// first-index search or the class-aware ratio scan, restated as order-independent
+// reductions (warp shuffle -> shared memory -> warp shuffle), so any tree order
+// returns the reference's sequential answer.  The work is O(n + m) against the
+// O(n*m) update, and the pivot column is gathered into a contiguous buffer on
+// the way so the streaming update never does a strided read.
+//
+// The same building blocks serve the column-sharded flow: `candidate` is the
+// local half of K1 (+ column gather into the all-gather message), `select` is
+// the global half of K1 (min key over ranks) + K2 on the winning column.
+#include "spx_common.cuh"
+
+namespace {
+
+using namespace spx;
+
+constexpr int PICK_THREADS = 1024;
+constexpr int PICK_WARPS   = PICK_THREADS / 32;
+constexpr int MSG_HEADER   = 4;      // doubles: [key_hi, key_lo, r_phase1, reserved]
+
+struct Scratch {
+    int                red_i[PICK_WARPS];
+    unsigned long long red_k[PICK_WARPS];
+    Ratio              red_q[PICK_WARPS];
+    int                out_i;
+    unsigned long long out_k;
+    Ratio              out_q;
+};
+
+__device__ __forceinline__ int block_min_int(int v, Scratch &s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_min_int(v);
+    if (lane == 0) s.red_i[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_min_int(s.red_i[lane]);
+        if (lane == 0) s.out_i = w;
+    }
+    __syncthreads();
+    const int out = s.out_i;
+    __syncthreads();
+    return out;
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, v, sft);
+        v = o < v ? o : v;
+    }
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, Scratch &s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_min_u64(v);
+    if (lane == 0) s.red_k[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = warp_min_u64(s.red_k[lane]);
+        if (lane == 0) s.out_k = w;
+    }
+    __syncthreads();
+    const unsigned long long out = s.out_k;
+    __syncthreads();
+    return out;
+}
+
+__device__ __forceinline__ Ratio block_ratio_reduce(Ratio q, Scratch &s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    q = warp_ratio_reduce(q);
+    if (lane == 0) s.red_q[warp] = q;
+    __syncthreads();
+    if (warp == 0) {
+        Ratio w = warp_ratio_reduce(s.red_q[lane]);
+        if (lane == 0) s.out_q = w;
+    }
+    __syncthreads();
+    const Ratio out = s.out_q;
+    __syncthreads();
+    return out;
+}
+
+struct IsNeg { __device__ bool operator()(double v) const { return v < 0.0; } };   // :74, :96
+struct IsPos { __device__ bool operator()(double v) const { return v > 0.0; } };   // :83
+
+// first j in [0, len) with pred(x[j]); chunked so the usual early hit costs one pass
+template <class Pred>
+__device__ int block_first_index(const double *__restrict__ x, int len, Pred pred, Scratch &s) {
+    for (int base = 0; base < len; base += PICK_THREADS * 4) {
+        int loc = SPX_NONE;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = base + u * PICK_THREADS + (int)threadIdx.x;
+            if (j < len && pred(x[j])) loc = min(loc, j);
+        }
+        loc = block_min_int(loc, s);
+        if (loc != SPX_NONE) return loc;
+    }
+    return SPX_NONE;
+}
+
+// K1 on the columns [0, m_loc) this CTA can see.
+//   r1    : phase-1 row (first b < 0, :72-76) or -1
+//   cloc  : entering column, local index, or SPX_NONE
+//   keyhi : 0 for the reference rule; the order-preserving image of f[cloc] for Dantzig
+__device__ void block_entering(const double *__restrict__ A, const double *__restrict__ b,
+                               int n, int m_loc, int64_t ld, int rule, const spx_state *st,
+                               Scratch &s, int &r1, int &cloc, unsigned long long &keyhi) {
+    const int64_t npiv = st->npiv;
+    const int sl = (int)(npiv & 1);
+    const bool hinted = (st->hint_tag[sl] == npiv);
+    keyhi = 0ull;
+    const int rb = hinted ? st->hint_bneg[sl] : block_first_index(b, n, IsNeg(), s);
+    if (rb != SPX_NONE) {                                              // :79
+        r1 = rb;
+        cloc = block_first_index(A + (int64_t)rb * ld, m_loc, IsPos(), s);   // :82-85
+        return;
+    }
+    r1 = -1;
+    const double *f = A + (int64_t)n * ld;
+    if (rule == SPX_RULE_REFERENCE) {                                  // :94-98
+        cloc = hinted ? st->hint_fneg[sl] : block_first_index(f, m_loc, IsNeg(), s);
+        return;
+    }
+    // Dantzig: most negative f[j], lowest index on ties
+    unsigned long long best = ~0ull;
+    for (int j = threadIdx.x; j < m_loc; j += PICK_THREADS) {
+        const double v = f[j];
+        if (v < 0.0) { const unsigned long long k = orderable(v); best = k < best ? k : best; }
+    }
+    best = block_min_u64(best, s);
+    if (best == ~0ull) { cloc = SPX_NONE; return; }
+    int loc = SPX_NONE;
+    for (int j = threadIdx.x; j < m_loc; j += PICK_THREADS) {
+        const double v = f[j];
+        if (v < 0.0 && orderable(v) == best) { loc = j; break; }
+    }
+    cloc = block_min_int(loc, s);
+    keyhi = best;
+}
+
+// K2 + bookkeeping once the entering column is known.
+//   col/stride : where the winning column lives (tableau: stride ld; message: stride 1)
+//   r1         : phase-1 row or -1;  cglob : global column index or -1 (none)
+__device__ void block_finish(const double *__restrict__ col, int64_t stride,
+                             const double *__restrict__ b, int n, int r1, int64_t cglob,
+                             spx_state *st, double *__restrict__ colbuf, Scratch &s) {
+    int status, r = -1;
+    double p = 0.0;
+    if (cglob < 0) {
+        status = (r1 >= 0) ? SPX_INCORRECT : SPX_OPTIMAL;              // :88-89, :101-103
+    } else {
+        Ratio q = ratio_identity();
+        for (int i = threadIdx.x; i <= n; i += PICK_THREADS) {
+            const double a = col[(int64_t)i * stride];
+            colbuf[i] = a;
+            if (r1 < 0 && i < n) ratio_accumulate(q, i, a, b[i]);      // :111-136
+        }
+        if (r1 >= 0) {
+            r = r1;                                                    // :91, no ratio test in phase 1
+        } else {
+            q = block_ratio_reduce(q, s);
+            bool elig_nan = false;
+            if (q.elig_row != SPX_NONE) {
+                const double v = __ddiv_rn(b[q.elig_row], col[(int64_t)q.elig_row * stride]);
+                elig_nan = (v != v);
+            }
+            r = ratio_decide(q, elig_nan);                             // :138-141
+        }
+        status = (r < 0) ? SPX_NOCONV : SPX_PIVOT;
+        if (status == SPX_PIVOT) {
+            p = col[(int64_t)r * stride];
+            if (st->npiv >= st->max_pivots) status = SPX_CAP;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->status = status;
+        st->phase1 = (r1 >= 0) ? 1 : 0;
+        if (status == SPX_PIVOT) {
+            st->r = r; st->c = cglob; st->p = p;
+            const int nslot = (int)((st->npiv + 1) & 1);
+            st->slot = nslot;
+            st->hint_bneg[nslot] = SPX_NONE;      // the update min-reduces into these
+            st->hint_fneg[nslot] = SPX_NONE;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PICK_THREADS, 1)
+pick_kernel(const double *__restrict__ A, const double *__restrict__ b, int n, int m, int64_t ld,
+            int rule, int sticky, spx_state *st, double *__restrict__ colbuf) {
+    __shared__ Scratch s;
+    if (sticky && st->status != SPX_PIVOT) return;
+    int r1, cloc; unsigned long long keyhi;
+    block_entering(A, b, n, m, ld, rule, st, s, r1, cloc, keyhi);
+    const int64_t cglob = (cloc == SPX_NONE) ? -1 : (int64_t)cloc;
+    block_finish(A + (cglob < 0 ? 0 : cglob), ld, b, n, r1, cglob, st, colbuf, s);
+}
+
+// local half of K1 for one column shard; message = [key_hi, key_lo, r1, 0 | column(n+1)]
+__global__ void __launch_bounds__(PICK_THREADS, 1)
+shard_candidate_kernel(const double *__restrict__ A, const double *__restrict__ b, int n, int m_loc,
+                       int64_t ld, int64_t col0, int rule, int sticky, const spx_state *st,
+                       double *__restrict__ msg) {
+    __shared__ Scratch s;
+    if (sticky && st->status != SPX_PIVOT) return;
+    int r1, cloc; unsigned long long keyhi;
+    block_entering(A, b, n, m_loc, ld, rule, st, s, r1, cloc, keyhi);
+    if (threadIdx.x == 0) {
+        unsigned long long *h = reinterpret_cast<unsigned long long *>(msg);
+        h[0] = (cloc == SPX_NONE) ? ~0ull : keyhi;
+        h[1] = (cloc == SPX_NONE) ? ~0ull : (unsigned long long)(col0 + cloc);
+        h[2] = (unsigned long long)(long long)r1;
+        h[3] = 0ull;
+    }
+    if (cloc != SPX_NONE) {
+        const double *col = A + cloc;
+        for (int i = threadIdx.x; i <= n; i += PICK_THREADS)
+            msg[MSG_HEADER + i] = col[(int64_t)i * ld];
+    }
+}
+
+// global half of K1 + K2 from the gathered messages of all ranks
+__global__ void __launch_bounds__(PICK_THREADS, 1)
+shard_select_kernel(const double *__restrict__ gathered, int nranks, int64_t msg_doubles,
+                    const double *__restrict__ b, int n, int sticky, spx_state *st,
+                    double *__restrict__ colbuf) {
+    __shared__ Scratch s;
+    if (sticky && st->status != SPX_PIVOT) return;
+    // every thread scans the (few) headers: lexicographic min of (key_hi, key_lo)
+    unsigned long long bh = ~0ull, bl = ~0ull; int win = -1;
+    for (int g = 0; g < nranks; ++g) {
+        const unsigned long long *h =
+            reinterpret_cast<const unsigned long long *>(gathered + (int64_t)g * msg_doubles);
+        const unsigned long long kh = h[0], kl = h[1];
+        if (kl != ~0ull && (win < 0 || kh < bh || (kh == bh && kl < bl))) { bh = kh; bl = kl; win = g; }
+    }
+    const int r1 = (int)(long long)reinterpret_cast<const unsigned long long *>(gathered)[2];
+    const int64_t cglob = (win < 0) ? -1 : (int64_t)bl;
+    const double *col = gathered + (int64_t)(win < 0 ? 0 : win) * msg_doubles + MSG_HEADER;
+    block_finish(col, 1, b, n, r1, cglob, st, colbuf, s);
+}
+
+} // namespace
+
+// ---- launchers (called from spx_api.cu) -------------------------------------
+namespace spx_launch {
+
+int64_t shard_msg_doubles(int n) {
+    int64_t d = MSG_HEADER + (int64_t)n + 1;
+    return (d + 15) / 16 * 16;
+}
+
+cudaError_t pick(const double *A, const double *b, int n, int m, int64_t ld, int rule, int sticky,
+                 spx_state *st, double *colbuf, cudaStream_t stream) {
+    pick_kernel<<<1, PICK_THREADS, 0, stream>>>(A, b, n, m, ld, rule, sticky, st, colbuf);
+    spx_host::count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t shard_candidate(const double *A, const double *b, int n, int m_loc, int64_t ld,
+                            int64_t col0, int rule, int sticky, const spx_state *st, double *msg,
+                            cudaStream_t stream) {
+    shard_candidate_kernel<<<1, PICK_THREADS, 0, stream>>>(A, b, n, m_loc, ld, col0, rule, sticky,
+                                                           st, msg);
+    spx_host::count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t shard_select(const double *gathered, int nranks, const double *b, int n, int sticky,
+                         spx_state *st, double *colbuf, cudaStream_t stream) {
+    shard_select_kernel<<<1, PICK_THREADS, 0, stream>>>(gathered, nranks, shard_msg_doubles(n), b,
+                                                        n, sticky, st, colbuf);
+    spx_host::count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace spx_launch

@@ -292,7 +292,7 @@ def make_cfg4():
     T = np.concatenate([rows.reshape(-1), c])
     del rows
     N = np.empty_like(T)
-    K = int(os.environ.get("CFG4_PIVOTS", "400"))
+    K = int(os.environ.get("CFG4_PIVOTS", "2000"))
     trace = []
     marks = {}
     t0 = time.time()
@@ -304,7 +304,7 @@ def make_cfg4():
         trace.append([r, cc])
         oracle.lib().orc_update(oracle._dp(T), oracle._dp(N), n, m, r, cc)
         T, N = N, T
-        if (k + 1) in (16, 50, 100, 200, 400, 800):
+        if (k + 1) in (16, 50, 100, 200, 400, 800, 1600, 2000):
             body = T[: n * (m + 1)].reshape(n, m + 1)
             marks[str(k + 1)] = {
                 "pivot_sha256": W.pivot_digest(trace),

@@ -1,0 +1,327 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the
+golden fixtures generated from the live reference.  Bit-exact everywhere: pivot
+sequences, labels and every fp64 cell; no tolerance is needed or used.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+from simplex_method_solver_b200 import workloads as W
+from util import END_TO_STATUS, bits, case_inputs, flat_of, label_codes, table_sha, unhex, unhex1
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def spx():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from simplex_method_solver_b200 import _native, batched, engine, simplex
+    _native.lib()
+
+    class NS:
+        pass
+    ns = NS()
+    ns.N, ns.batched, ns.engine, ns.simplex, ns.torch = _native, batched, engine, simplex, torch
+    return ns
+
+
+# --------------------------------------------------------------------------- get_solution()
+def _check_infos(spx, case, engine):
+    rows, c = case_inputs(case)
+    sm = spx.simplex.SimplexMethod(rows.tolist(), c.tolist(), engine=engine)
+    got = sm.get_solution()
+    exp = case["get_solution"]
+    assert len(got) == len(exp), case["name"]
+    for g, e in zip(got, exp):
+        if "error" in e:
+            assert isinstance(g, spx.simplex.Error) and str(g) == e["error"], case["name"]
+            continue
+        assert isinstance(g, spx.simplex.Info)
+        assert g.row == e["row"] and g.column == e["column"], case["name"]
+        assert g.i == e["i"] and g.j == e["j"], case["name"]
+        assert len(g.table) == len(e["table"])
+        for gr, er in zip(g.table, e["table"]):
+            assert [float(v).hex() for v in gr] == er, case["name"]
+        assert float(g.x1).hex() == e["x1"] and float(g.x2).hex() == e["x2"], case["name"]
+        assert float(g.optimum).hex() == e["optimum"], case["name"]
+    # object state after the call matches the reference's (final labels / table)
+    assert sm.row == case["row_labels"] and sm.column == case["column_labels"]
+    assert [[float(v).hex() for v in r] for r in sm.table] == case["final_table"]
+
+
+@pytest.mark.parametrize("engine", ["warp", "stream"])
+def test_get_solution_matches_reference_snapshots(spx, ref_cases, engine):
+    cases = [c for c in ref_cases if "get_solution" in c]
+    assert len(cases) >= 15
+    for case in cases:
+        _check_infos(spx, case, engine)
+
+
+def test_cfg1_snapshot_digest(spx, ref_cases):
+    case = next(c for c in ref_cases if c["name"] == "ref_example_cfg1_205")
+    sm = spx.simplex.SimplexMethod(W.CFG1_ROWS, W.CFG1_C)
+    res = sm.get_solution()
+    assert [(i.i, i.j) for i in res[:-1]] == [(2, 0), (3, 0), (1, 1), (0, 0)]
+    assert W.snapshot_digest([i.table for i in res]) == case["snapshot_sha256"]
+    assert case["snapshot_sha256"] == "0599fb0b6881268191a0d0490575cbe5891d0e5f5f7148bd4124e07a0a853183"
+    assert (res[-1].x1, res[-1].x2) == (39.18192919380969, 26.096639697976617)
+    assert res[-1].optimum == -65.2785688917863
+
+
+# --------------------------------------------------------------------------- all golden cases
+def test_all_reference_cases_streaming_solver(spx, ref_cases):
+    """solve(): device-side pick+update loop; trace, ending, labels, final table bits."""
+    for case in ref_cases:
+        rows, c = case_inputs(case)
+        n, m = rows.shape[0], rows.shape[1] - 1
+        sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
+        sol = sm.solve(max_pivots=case["cap"], chunk=7)
+        assert sol.status == END_TO_STATUS[case["end"]], case["name"]
+        assert sol.trace.tolist() == case["trace"], case["name"]
+        flat = sm._dev.export_flat(sm._npiv)
+        assert table_sha(flat) == case["final_table_sha256"], case["name"]
+        assert sm.row == case["row_labels"] and sm.column == case["column_labels"], case["name"]
+        if "x1" in case:
+            x1, x2 = sm.find_optimum()
+            assert float(x1).hex() == case["x1"] and float(x2).hex() == case["x2"], case["name"]
+            assert float(sm.f(x1, x2)).hex() == case["f"], case["name"]
+            assert float(sol.obj2).hex() == case["f"], case["name"]
+
+
+def test_all_reference_cases_batched_solver(spx, ref_cases):
+    """solve_batched(): same cases grouped by shape, one warp per LP."""
+    groups = {}
+    for case in ref_cases:
+        rows, c = case_inputs(case)
+        key = (rows.shape[0], rows.shape[1] - 1, case["cap"])
+        groups.setdefault(key, []).append((case, flat_of(rows, c)))
+    for (n, m, cap), items in groups.items():
+        tables = np.stack([f for _, f in items])
+        res = spx.batched.solve_batched(tables, n, m, max_pivots=cap)
+        for k, (case, _) in enumerate(items):
+            assert res.status[k] == END_TO_STATUS[case["end"]], case["name"]
+            assert res.npiv[k] == len(case["trace"]), case["name"]
+            assert res.trace[k, : res.npiv[k]].tolist() == case["trace"], case["name"]
+            assert table_sha(res.tables[k]) == case["final_table_sha256"], case["name"]
+            assert res.rowlab[k].tolist() == label_codes(case["row_labels"][:-1], m), case["name"]
+            assert res.collab[k].tolist() == label_codes(case["column_labels"][:-1], m), case["name"]
+            if "x1" in case:
+                assert float(res.x[k, 0]).hex() == float(float.fromhex(case["x1"])).hex()
+                assert float(res.x[k, 1]).hex() == float(float.fromhex(case["x2"])).hex()
+                assert float(res.obj[k]).hex() == case["f"], case["name"]
+
+
+# --------------------------------------------------------------------------- step API
+def test_step_api_matches_oracle(spx):
+    rng = np.random.default_rng(7)
+    for t in range(40):
+        n, m = int(rng.integers(1, 12)), int(rng.integers(2, 9))
+        A = rng.integers(-3, 4, (n, m)).astype(float)
+        b = rng.integers(-2, 7, n).astype(float)
+        c = rng.integers(-3, 4, m).astype(float)
+        rows = np.hstack([A, b[:, None]])
+        sm = spx.simplex.SimplexMethod(rows.tolist(), c.tolist())
+        T = flat_of(rows, c)
+        for step in range(30):
+            st, r, cc, e = oracle.pick(T, n, m)
+            if st == oracle.PIVOT:
+                assert sm.pick_element() == (True, r, cc, e)
+                sm.recalculate_matrix()
+                T = oracle.update(T, n, m, r, cc)
+                got = np.asarray([v for row in sm.table for v in row])
+                assert np.array_equal(bits(got), bits(T))
+            elif st == oracle.OPTIMAL:
+                ok, x1, x2, f = sm.pick_element()
+                assert ok is False
+                assert sm.recalculate_matrix() is None
+                break
+            else:
+                with pytest.raises(ValueError, match=oracle.STATUS_NAME[st]):
+                    sm.pick_element()
+                with pytest.raises(ValueError, match=oracle.STATUS_NAME[st]):
+                    sm.recalculate_matrix()
+                break
+
+
+def test_inputs_not_mutated_and_attributes(spx):
+    rows = [[-1.0, -1.0, 10.0], [1.0, -2.0, 4.0]]
+    c = [-1.0, -5.0]
+    keep = ([list(r) for r in rows], list(c))
+    sm = spx.simplex.SimplexMethod(rows, c)
+    assert (sm.n, sm.m, sm.invalid_index) == (2, 2, 3)
+    assert sm.function is c
+    assert sm.row == ["x1", "x2", "-b"] and sm.column == ["y1", "y2", "f"]
+    assert len(sm.table) == 3 and len(sm.table[-1]) == 2 and sm.table[0] == rows[0]
+    sm.get_solution()
+    assert (rows, c) == keep
+
+
+def test_cycling_input_hits_cap(spx):
+    sm = spx.simplex.SimplexMethod([[1, 0, 3], [2, 0, 0]], [-1, 0], max_pivots=25)
+    res = sm.get_solution()
+    assert isinstance(res[-1], spx.simplex.Error) and str(res[-1]) == "pivot limit reached"
+    assert [(i.i, i.j) for i in res[:-2]] == [(1, 0)] * 25
+
+
+# --------------------------------------------------------------------------- unit: K1/K2/K3 on ragged shapes
+@pytest.mark.parametrize("n,m", [(1, 2), (3, 1), (7, 15), (8, 16), (9, 17), (63, 511), (64, 512),
+                                 (65, 513), (130, 1030), (257, 100), (40, 2049)])
+def test_pick_update_bit_exact_ragged_shapes(spx, n, m):
+    """One pick + one update per step vs the oracle, whole table compared bit for bit."""
+    rng = np.random.default_rng(n * 1000 + m)
+    rows, c = W.dense_lp(n, m, seed=n + m)
+    # sprinkle exact zeros and sign changes so every branch of the ratio scan is reachable
+    rows[rng.random(rows.shape) < 0.05] = 0.0
+    if n > 2:
+        rows[rng.integers(0, n), m] = 0.0
+    dev = spx.engine.DeviceTableau(n, m, trace_capacity=64)
+    dev.load(rows, c, max_pivots=64)
+    T = flat_of(rows, c)
+    npiv = 0
+    for step in range(12):
+        st, r, cc, e = oracle.pick(T, n, m)
+        dev.pick(npiv)
+        s = dev.read_state()
+        assert s.status == st
+        if st != oracle.PIVOT:
+            break
+        assert (s.r, s.c, s.p) == (r, cc, e)
+        dev.update(npiv)
+        npiv += 1
+        T = oracle.update(T, n, m, r, cc)
+        got = dev.export_flat(npiv)
+        assert np.array_equal(bits(got), bits(T)), f"step {step}"
+        assert dev.read_state().npiv == npiv
+
+
+def test_ratio_scan_special_values(spx):
+    """inf / NaN / signed zero in the ratio scan: same leaving row as the sequential reference scan."""
+    inf, nan = float("inf"), float("nan")
+    cases = [
+        [[-1, 0, 5], [-2, 0, inf], [-1, 0, 5]],
+        [[-1, 0, nan], [-2, 0, 4], [-1, 0, 5]],       # first eligible ratio NaN -> it wins
+        [[-1, 0, 5], [-2, 0, nan], [-1, 0, 5]],       # later NaN ignored
+        [[-0.0, 0, 5], [-2, 0, 0.0], [2, 0, -0.0]],
+        [[-1, 0, 0.0], [1, 0, 0.0], [-1, 0, 5]],
+        [[-inf, 0, 5], [-1, 0, 7]],
+        [[1e-320, 0, 5], [-1e-320, 0, 5]],
+    ]
+    for rows in cases:
+        rows = np.asarray(rows, dtype=np.float64)
+        c = np.asarray([-1.0, 0.0])
+        # keep b >= 0 so the phase-2 branch is taken where possible
+        n, m = rows.shape[0], 2
+        T = flat_of(rows, c)
+        st, r, cc, e = oracle.pick(T, n, m)
+        dev = spx.engine.DeviceTableau(n, m)
+        dev.load(rows, c)
+        dev.pick(0)
+        s = dev.read_state()
+        assert s.status == st, rows
+        if st == oracle.PIVOT:
+            assert (s.r, s.c) == (r, cc), rows
+        res = spx.batched.solve_batched(T[None, :], n, m, max_pivots=1)
+        o = oracle.solve_flat(T, n, m, max_pivots=1)
+        assert res.status[0] == o.status and res.npiv[0] == o.npiv
+        assert res.trace[0, : o.npiv].tolist() == o.trace.tolist()
+        # NaN sign/payload is not defined by the reference (CPython) — NaN == NaN here
+        both_nan = np.isnan(res.tables[0]) & np.isnan(o.table)
+        assert (both_nan | (bits(res.tables[0]) == bits(o.table))).all()
+
+
+# --------------------------------------------------------------------------- BASELINE configs
+def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests):
+    g = cfg_digests["cfg2"]
+    rows, c = W.dense_lp(1000, 2000, 0)
+    assert W.input_digest(rows, c) == g["input_sha256"]
+    sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
+    # the reference's own first 12 pivots and its table after them
+    sol = sm.solve(max_pivots=12, chunk=12)
+    assert sol.trace.tolist() == g["reference_first12"]["trace"]
+    assert table_sha(sm._dev.export_flat(sm._npiv)) == g["reference_first12"]["table_sha256_after12"]
+    # continue to optimality
+    sol = sm.solve(max_pivots=200000 - 12, chunk=256)
+    o = g["oracle_full"]
+    assert sol.status == o["status"] == 0 and sol.npiv == o["npiv"] == 13579
+    assert W.pivot_digest(sol.trace[:100]) == o["pivot_sha256_after100"]
+    assert W.pivot_digest(sol.trace[:1000]) == o["pivot_sha256_after1000"]
+    assert W.pivot_digest(sol.trace) == o["pivot_sha256_final"]
+    assert table_sha(sm._dev.export_flat(sm._npiv)) == o["final_table_sha256"]
+    assert hashlib.sha256(sol.x.astype("<f8").tobytes()).hexdigest() == o["x_sha256"]
+    assert float(sol.objective).hex() == o["objm"] and float(sol.obj2).hex() == o["obj2"]
+    assert hashlib.sha256(sol.collab.astype("<i4").tobytes()).hexdigest() == o["collab_sha256"]
+    assert hashlib.sha256(sol.rowlab.astype("<i4").tobytes()).hexdigest() == o["rowlab_sha256"]
+
+
+def test_cfg3_batched_65536(spx, cfg_digests):
+    g = cfg_digests["cfg3"]
+    T, C = W.gui_batch(65536, 0)
+    assert W.input_digest(T, C) == g["input_sha256"]
+    res = spx.batched.solve_batched(W.batch_flat(T, C), 8, 2, max_pivots=64)
+    assert (res.status == 0).all()
+    hist = {str(k): int(v) for k, v in zip(*np.unique(res.npiv, return_counts=True))}
+    assert hist == g["pivot_histogram"]
+    assert int(res.npiv.sum()) == g["total_pivots"] == 408212
+    assert W.batch_pivot_digest(res.trace, res.npiv) == g["batch_pivot_sha256"]
+    assert W.batch_solution_digest(res.x[:, 0], res.x[:, 1], res.obj) == g["batch_solution_sha256"]
+    for k, e in enumerate(g["first256"]):
+        assert res.trace[k, : res.npiv[k]].tolist() == e["trace"]
+        assert table_sha(res.tables[k]) == e["final_table_sha256"]
+
+
+@pytest.mark.parametrize("n", [10, 20])
+def test_cfg5_klee_minty(spx, cfg_digests, n):
+    g = cfg_digests[f"km{n}"]
+    rows, c = W.klee_minty(n)
+    cap = 1 << n
+    res = spx.batched.solve_batched(flat_of(rows, c)[None, :], n, n, max_pivots=cap)
+    assert res.status[0] == 0 and res.npiv[0] == g["npiv"] == (1 << n) - 1
+    tr = res.trace[0, : res.npiv[0]]
+    assert tr[:8].tolist() == g["first8"]
+    assert W.pivot_digest(tr) == g["pivot_sha256"]
+    assert table_sha(res.tables[0]) == g["final_table_sha256"]
+    assert res.rowlab[0].tolist() == label_codes(g["row_labels"][:-1], n)
+    assert res.collab[0].tolist() == label_codes(g["column_labels"][:-1], n)
+    assert float(res.x[0, 0]).hex() == float(float.fromhex(g["x1"])).hex()
+    assert float(res.obj[0]).hex() == g["f"]
+    assert res.x[0, n - 1] == float(5 ** n) and (res.x[0, : n - 1] == 0).all()
+
+
+def test_cfg5_klee_minty10_streaming_equals_batched(spx, cfg_digests):
+    rows, c = W.klee_minty(10)
+    sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
+    sol = sm.solve(max_pivots=2000, chunk=128)
+    assert sol.status == 0 and sol.npiv == 1023
+    assert W.pivot_digest(sol.trace) == cfg_digests["km10"]["pivot_sha256"]
+    assert table_sha(sm._dev.export_flat(sm._npiv)) == cfg_digests["km10"]["final_table_sha256"]
+
+
+def test_cfg4_16k_x_32k_prefix(spx, cfg_digests):
+    """The 4.3 GB tableau: first 200 pivots against the oracle-generated golden prefix."""
+    g = cfg_digests["cfg4"]
+    n, m = 16384, 32768
+    rows, c = W.dense_lp(n, m, 0)
+    assert W.input_digest(rows, c) == g["input_sha256"]
+    dev = spx.engine.DeviceTableau(n, m, trace_capacity=200)
+    dev.load(rows, c, max_pivots=200)
+    del rows
+    dev.pick(0)
+    s = dev.read_state()
+    assert (s.r, s.c) == tuple(g["trace"][0]) and float(s.p).hex() == g["first_pivot_value"]
+    done = 0
+    for mark in (16, 50, 100, 200):
+        status, npiv = dev.solve(chunk=mark - done, stop_after=mark - done)
+        done = mark
+        assert npiv == mark and status == spx.N.PIVOT
+        tr = dev.trace[:mark].cpu().numpy()
+        assert tr.tolist() == g["trace"][:mark]
+        assert W.pivot_digest(tr) == g["marks"][str(mark)]["pivot_sha256"]
+        b = dev.b_host(npiv)
+        f = dev.A[dev.cur(npiv), n, :m].cpu().numpy()
+        assert [float(v).hex() for v in b[:4]] == g["marks"][str(mark)]["b_first4"]
+        assert [float(v).hex() for v in f[:4]] == g["marks"][str(mark)]["f_first4"]
+        assert hashlib.sha256(b.tobytes()).hexdigest() == g["marks"][str(mark)]["b_sha256"]
+        assert hashlib.sha256(f.tobytes()).hexdigest() == g["marks"][str(mark)]["f_sha256"]
