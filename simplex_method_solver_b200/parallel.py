@@ -1,0 +1,217 @@
+"""Multi-GPU paths: one process per GPU, ``torch.distributed`` for the plumbing.
+
+Two partitionings, the two places where the pivot loop shards naturally
+(SURVEY.md §8e):
+
+* **Batches of independent small LPs** — contiguous split of the batch, no
+  data-path collective (``shard_range`` + ``solve_batched_sharded``).
+
+* **Column-sharded large tableau** — rank g owns a contiguous block of body
+  columns as its own split matrix; the b column, labels and the 128-byte solver
+  state are replicated.  One exchange per pivot: every rank packs
+  ``[key | its candidate entering column]`` (K1 local half) and a single
+  all-gather over NCCL/NVLink delivers all candidates everywhere; each rank
+  then takes the lexicographic-min key (K1 global half), runs the ratio test on
+  the winning column with its replica of b (K2, redundantly — bit-identical on
+  all ranks) and updates its own columns (K3).  No host round trip, no
+  data-dependent broadcast root.  The pivot trace equals the single-GPU trace
+  exactly (tests/test_sharded_gloo.py on CPU with gloo; bench.py on GPUs).
+
+The kernels are reached through ``ShardOps``; the product implementation
+(``CudaShardOps``) calls the C ABI.  Tests inject a CPU stand-in to exercise
+this file's collective logic under gloo without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+
+MSG_HEADER = 4     # doubles: [key_hi, key_lo, r_phase1, reserved] (csrc/spx_pick.cu)
+TILE_COLS = 512    # column tile of the update kernel (csrc/spx_update.cu)
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Contiguous split of `total` units: (start, count) of `rank`; sizes differ by at most 1."""
+    base, rem = divmod(int(total), int(world))
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+def column_block(m: int, rank: int, world: int, align: int = TILE_COLS):
+    """Column block of `rank`: contiguous, boundaries on multiples of `align` (whole update tiles)."""
+    tiles = -(-int(m) // align)
+    t0, tc = shard_range(tiles, rank, world)
+    col0 = min(t0 * align, m)
+    col1 = min((t0 + tc) * align, m)
+    return col0, col1 - col0
+
+
+def msg_doubles(n: int) -> int:
+    return (MSG_HEADER + n + 1 + 15) // 16 * 16
+
+
+class CudaShardOps:
+    """The three per-pivot kernels of the sharded flow, through the C ABI."""
+
+    def __init__(self, device):
+        N.lib()
+        self.device = torch.device(device)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def import_shard(self, rows, function, A, b, n, m, col0, m_loc, ld):
+        N.call("spx_import_shard", rows.ctypes.data, function.ctypes.data, A.data_ptr(), b.data_ptr(),
+               n, m, col0, m_loc, ld, self._stream())
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def init_state(self, state, rowlab, collab, n, m, max_pivots):
+        N.call("spx_init_state", state.data_ptr(), rowlab.data_ptr(), collab.data_ptr(), n, m,
+               max_pivots, self._stream())
+
+    def candidate(self, A, b, n, m_loc, ld, col0, rule, state, send):
+        N.call("spx_shard_candidate", A.data_ptr(), b.data_ptr(), n, m_loc, ld, col0, rule, 1,
+               state.data_ptr(), send.data_ptr(), self._stream())
+
+    def select(self, gathered, world, b, n, rule, state, colbuf):
+        N.call("spx_shard_select", gathered.data_ptr(), world, b.data_ptr(), n, rule, 1,
+               state.data_ptr(), colbuf.data_ptr(), self._stream())
+
+    def update(self, Ain, Aout, bin_, bout, n, m_loc, ld, col0, state, colbuf, rowlab, collab, trace):
+        N.call("spx_shard_update", Ain.data_ptr(), Aout.data_ptr(), bin_.data_ptr(), bout.data_ptr(),
+               n, m_loc, ld, col0, state.data_ptr(), colbuf.data_ptr(), rowlab.data_ptr(),
+               collab.data_ptr(), N.ptr(trace), self._stream())
+
+
+class ShardedTableau:
+    """One rank's share of a column-sharded tableau plus the replicated pieces."""
+
+    def __init__(self, n: int, m: int, rank: int, world: int, device, trace_capacity: int = 0,
+                 group=None, ops=None, rule: int = N.RULE_REFERENCE):
+        self.n, self.m, self.rank, self.world = int(n), int(m), int(rank), int(world)
+        self.device = torch.device(device)
+        self.group = group
+        self.rule = rule
+        self.ops = ops if ops is not None else CudaShardOps(self.device)
+        self.col0, self.m_loc = column_block(self.m, self.rank, self.world)
+        self.ld = max(16, (self.m_loc + 15) // 16 * 16)
+        self.nb = (self.n + 15) // 16 * 16
+        dev = self.device
+        f64, i32 = torch.float64, torch.int32
+        self.A = torch.zeros((2, self.n + 1, self.ld), dtype=f64, device=dev)
+        self.b = torch.zeros((2, self.nb), dtype=f64, device=dev)
+        self.colbuf = torch.zeros((self.n + 1 + 63) // 64 * 64 + 64, dtype=f64, device=dev)
+        self.state = torch.zeros(ctypes.sizeof(N.SpxState) // 8, dtype=torch.int64, device=dev)
+        self.rowlab = torch.zeros(self.m, dtype=i32, device=dev)
+        self.collab = torch.zeros(max(self.n, 1), dtype=i32, device=dev)
+        self.msgd = msg_doubles(self.n)
+        self.send = torch.zeros(self.msgd, dtype=f64, device=dev)
+        self.gathered = torch.zeros((self.world, self.msgd), dtype=f64, device=dev)
+        self.trace = torch.zeros((trace_capacity, 2), dtype=i32, device=dev) if trace_capacity > 0 else None
+        self.npiv_enqueued = 0
+
+    def load(self, rows: np.ndarray, function: np.ndarray, max_pivots: int):
+        """Every rank reads its own column block (and the whole b column) of the same host table."""
+        assert rows.shape == (self.n, self.m + 1) and rows.dtype == np.float64 and rows.flags.c_contiguous
+        self.ops.import_shard(rows, np.ascontiguousarray(function, dtype=np.float64), self.A[0], self.b[0],
+                              self.n, self.m, self.col0, self.m_loc, self.ld)
+        self.ops.init_state(self.state, self.rowlab, self.collab, self.n, self.m, int(max_pivots))
+        self.npiv_enqueued = 0
+
+    def step(self):
+        """One pivot: candidate -> all-gather -> select -> update.  Asynchronous on a GPU."""
+        cur = self.npiv_enqueued & 1
+        self.ops.candidate(self.A[cur], self.b[cur], self.n, self.m_loc, self.ld, self.col0, self.rule,
+                           self.state, self.send)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered.view(-1), self.send, group=self.group)
+        else:
+            self.gathered[0].copy_(self.send)
+        self.ops.select(self.gathered, self.world, self.b[cur], self.n, self.rule, self.state, self.colbuf)
+        self.ops.update(self.A[cur], self.A[cur ^ 1], self.b[cur], self.b[cur ^ 1], self.n, self.m_loc,
+                        self.ld, self.col0, self.state, self.colbuf, self.rowlab, self.collab, self.trace)
+        self.npiv_enqueued += 1
+
+    def run(self, pivots: int, check_every: int = 0):
+        """Enqueue `pivots` pivots; with check_every > 0 stop early on a terminal status.
+
+        Buffer parity follows the number of pivots actually applied, so after an
+        early stop the enqueue counter is re-synchronised from the device state.
+        """
+        done = 0
+        while done < pivots:
+            k = pivots - done if check_every <= 0 else min(check_every, pivots - done)
+            for _ in range(k):
+                self.step()
+            done += k
+            if check_every > 0:
+                st = self.read_state()
+                if st.status != N.PIVOT:
+                    self.npiv_enqueued = int(st.npiv)
+                    return st
+        return None
+
+    def read_state(self) -> N.SpxState:
+        host = self.state.cpu().numpy()
+        st = N.SpxState.from_buffer_copy(host.tobytes())
+        return st
+
+    def solve(self, max_pivots: int, check_every: int = 64):
+        """Pivot to a terminal status; returns (status, npiv).
+
+        The cap lives in the device state (set by load()): once npiv reaches it the next
+        select reports SPX_CAP — or the real ending if the table is terminal at that point —
+        exactly as the single-GPU pick does, and every later kernel of the chunk is a no-op.
+        `max_pivots` only bounds the host loop against a state that was loaded with a larger cap.
+        """
+        while True:
+            st = self.run(check_every, check_every=check_every)
+            if st is None:
+                st = self.read_state()
+            if st.status == N.PIVOT and st.npiv >= st.max_pivots:
+                self.npiv_enqueued = int(st.npiv)
+                self.step()                      # the select of this step reports the ending
+                st = self.read_state()
+            if st.status != N.PIVOT or st.npiv >= max_pivots:
+                self.npiv_enqueued = int(st.npiv)
+                return int(st.status), int(st.npiv)
+
+    def sync(self) -> N.SpxState:
+        """Read the device state and re-derive the ping-pong parity from the pivots applied."""
+        st = self.read_state()
+        self.npiv_enqueued = int(st.npiv)
+        return st
+
+    def local_body(self) -> torch.Tensor:
+        """This rank's current columns [(n+1), m_loc] (row n = f)."""
+        self.sync()
+        return self.A[self.npiv_enqueued & 1, :, : self.m_loc]
+
+    def b_current(self) -> torch.Tensor:
+        self.sync()
+        return self.b[self.npiv_enqueued & 1, : self.n]
+
+
+def solve_batched_sharded(tables: np.ndarray, n: int, m: int, max_pivots: int = 64, rule: str = "reference",
+                          rank: Optional[int] = None, world: Optional[int] = None, device=None,
+                          solver=None):
+    """Each rank solves its contiguous share of the batch; no collective on the data path.
+
+    Returns (start, count, BatchResult) for this rank.  `solver` defaults to the CUDA
+    ``solve_batched``; tests pass a stand-in.
+    """
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    start, count = shard_range(tables.shape[0], rank, world)
+    if solver is None:
+        from .batched import solve_batched as solver
+    res = solver(tables[start:start + count], n, m, max_pivots=max_pivots, rule=rule, device=device)
+    return start, count, res
