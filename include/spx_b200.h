@@ -89,6 +89,19 @@ int         spx_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_mi
 /* kernels of this library launched since the last call with reset != 0 (bench.py's gpu_launches) */
 int64_t     spx_launch_count(int reset);
 
+/* process-wide tuning knobs; every setting computes bit-identical results */
+#define SPX_OPT_UPDATE_KERNEL    1  /* 0 auto (by body size), 1 tiled, 2 persistent TMA-pipelined */
+#define SPX_OPT_TILED_MIN_BLOCKS 2  /* tiled kernel: resident CTAs per SM the register budget targets (1..4) */
+#define SPX_OPT_PIPE_ORDER       3  /* pipelined kernel tile order: 0 chunked column-major, 1 interleaved row-major */
+#define SPX_OPT_PIPE_GRID        4  /* pipelined kernel CTAs (0 = one per SM) */
+int         spx_set_option(int32_t option, int64_t value);
+int64_t     spx_get_option(int32_t option);
+/* Device self-test of the hoisted-reciprocal division used by K3 against the
+ * compiler's div.rn.f64: for k < count compares d_a[k] / d_p[k % np]; returns the
+ * number of bit mismatches in *h_mismatches (and the first offending pair). */
+int         spx_selftest_division(const double *d_a, const double *d_p, int64_t count, int64_t np,
+                                  uint64_t *h_mismatches, double *h_first_bad, void *stream);
+
 /* ---- layout conversion (SimplexMethod.__init__, simplex.py:25-39) -------- */
 /* src_rows is the reference's `constraints` as a dense row-major [n][m+1] fp64
  * array, src_function its `function` [m]; both host or device

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libspx_b200.so")
 
 PIVOT, OPTIMAL, INCORRECT, NOCONV, CAP = 1, 0, -1, -2, -3
 RULE_REFERENCE, RULE_DANTZIG = 0, 1
+OPT_UPDATE_KERNEL, OPT_TILED_MIN_BLOCKS, OPT_PIPE_ORDER, OPT_PIPE_GRID = 1, 2, 3, 4
 RULES = {"reference": RULE_REFERENCE, "bland": RULE_REFERENCE, "dantzig": RULE_DANTZIG}
 
 # the two ValueError texts of pick_element(), /root/reference/src/simplex.py:89,139
@@ -54,6 +55,10 @@ SIGNATURES = {
     "spx_state_bytes": (ctypes.c_int, []),
     "spx_device_info": (ctypes.c_int, [_pi32, _pi32, _pi32]),
     "spx_launch_count": (_i64, [ctypes.c_int]),
+    "spx_set_option": (ctypes.c_int, [_i32, _i64]),
+    "spx_get_option": (_i64, [_i32]),
+    "spx_selftest_division": (ctypes.c_int, [_vp, _vp, _i64, _i64, ctypes.POINTER(ctypes.c_uint64),
+                                             ctypes.POINTER(ctypes.c_double), _vp]),
     "spx_import_table": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp]),
     "spx_import_shard": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i64, _vp]),
     "spx_export_table": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp]),

@@ -24,6 +24,10 @@ cudaError_t update(const double *, double *, const double *, double *, int, int,
                    spx_state *, const double *, int32_t *, int32_t *, int32_t *, cudaStream_t);
 cudaError_t extract(const double *, int, int, const int32_t *, const double *, double *, double *,
                     cudaStream_t);
+int64_t get_option(int);
+int     set_option(int, int64_t);
+cudaError_t selftest_division(const double *, const double *, int64_t, int64_t, unsigned long long *,
+                              double *, cudaStream_t);
 cudaError_t init_state(spx_state *, int32_t *, int32_t *, int, int, int64_t, cudaStream_t);
 cudaError_t solve_batched(double *, int64_t, int, int, int, int, double *, double *, int32_t *,
                           int32_t *, int32_t *, int32_t *, int32_t *, double *, cudaStream_t);
@@ -98,6 +102,41 @@ int64_t spx_launch_count(int reset) {
     long long v = spx_host::g_launches.load(std::memory_order_relaxed);
     if (reset) spx_host::g_launches.store(0, std::memory_order_relaxed);
     return v;
+}
+
+int spx_set_option(int32_t option, int64_t value) {
+    if (spx_launch::set_option(option, value) != 0) {
+        set_error("spx_set_option: bad option %d / value %lld", option, (long long)value);
+        return -2;
+    }
+    return 0;
+}
+
+int64_t spx_get_option(int32_t option) { return spx_launch::get_option(option); }
+
+int spx_selftest_division(const double *d_a, const double *d_p, int64_t count, int64_t np,
+                          uint64_t *h_mismatches, double *h_first_bad, void *stream) {
+    SPX_REQUIRE(d_a && d_p && h_mismatches && count >= 0 && np >= 1, "spx_selftest_division: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    unsigned long long *d_cnt = nullptr;
+    double *d_bad = nullptr;
+    if (check(cudaMalloc(&d_cnt, sizeof(*d_cnt)), "cudaMalloc")) return -1;
+    if (check(cudaMalloc(&d_bad, 2 * sizeof(double)), "cudaMalloc")) { cudaFree(d_cnt); return -1; }
+    int rc = 0;
+    double bad[2] = {0.0, 0.0};
+    unsigned long long cnt = 0;
+    if (check(cudaMemsetAsync(d_cnt, 0, sizeof(*d_cnt), s), "memset") ||
+        check(cudaMemsetAsync(d_bad, 0, 2 * sizeof(double), s), "memset") ||
+        check(spx_launch::selftest_division(d_a, d_p, count, np, d_cnt, d_bad, s), "selftest launch") ||
+        check(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s), "read") ||
+        check(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, s), "read") ||
+        check(cudaStreamSynchronize(s), "sync"))
+        rc = -1;
+    cudaFree(d_cnt);
+    cudaFree(d_bad);
+    *h_mismatches = cnt;
+    if (h_first_bad) { h_first_bad[0] = bad[0]; h_first_bad[1] = bad[1]; }
+    return rc;
 }
 
 // ---- layout conversion ---------------------------------------------------------

@@ -4,17 +4,28 @@
 // Memory-bound fp64 stream: every body cell is read once (8 B) and written once
 // (8 B) — the 16 B/cell/pivot of BASELINE.json — out of place between two
 // ping-pong buffers, so there is no hazard and the pivot row/column are
-// immutable for the whole pivot.
+// immutable for the whole pivot.  Per cell: 2 DMUL + 1 DADD for t*p - rj*ci and
+// 1 DMUL + 2 DFMA for the division by the pivot (reciprocal hoisted, see
+// pivot_div in spx_common.cuh) = 6 fp64 issues against 16 B of traffic.
 //
-// Mapping: a CTA owns a tile of TR rows x 512 columns; a thread owns two adjacent
-// columns (one 128-bit access per row) and walks down the rows, so
-//   - every warp access is a fully coalesced 512-byte line group,
-//   - the thread's two pivot-row values live in registers for the whole tile,
-//   - the column multiplier of a row is one shared-memory broadcast.
-// The 512-column slice of the pivot row and the TR-row slice of the gathered
-// pivot column are staged into shared memory with two cp.async.bulk (TMA, SASS
-// UBLKCP) copies completing on one mbarrier.  8 rows are loaded before the first
-// is consumed: 128 B in flight per thread.
+// Two kernels, same arithmetic, same results:
+//
+//  update_tiled_kernel      one CTA per tile of TR rows x 512 columns; a thread
+//      owns two adjacent columns (one 128-bit access per row) and walks down the
+//      rows: fully coalesced 512-byte line groups, the thread's two pivot-row
+//      values in registers, the column multiplier a shared-memory broadcast.  The
+//      pivot-row slice and the pivot-column slice are staged with two
+//      cp.async.bulk (TMA, SASS UBLKCP) copies on one mbarrier.  Used for tableaus
+//      that fit L2 (latency-bound: many small CTAs, 8 rows in flight per thread).
+//
+//  update_pipelined_kernel  persistent, warp-specialised, one CTA per SM: a
+//      producer lane streams tiles of 8 rows x 512 columns (32 KB) into a 6-stage
+//      shared-memory ring with cp.async.bulk (each stage also carries its slice of
+//      the pivot column and, when the column tile changes, of the pivot row);
+//      8 consumer warps read the stage with conflict-free 128-bit LDS, release it,
+//      compute and store straight to HBM with 128-bit streaming stores.  Up to
+//      ~190 KB of reads in flight per SM independent of register count: the HBM
+//      streaming path for tableaus larger than L2.
 //
 // Fused into the same pass: the b ('-b') column update, the label swap
 // (:152), the pivot trace, and the pricing of the NEXT pivot (first negative
@@ -31,13 +42,59 @@ constexpr int UPD_TC      = 2 * UPD_THREADS;   // columns per tile
 constexpr int UPD_TR_MAX  = 64;                // rows per tile (upper bound; multiple of 8)
 constexpr int UPD_UNROLL  = 8;
 
-__global__ void __launch_bounds__(UPD_THREADS)
-update_kernel(const double *__restrict__ Ain, double *__restrict__ Aout,
-              const double *__restrict__ bin, double *__restrict__ bout,
-              int n, int m_loc, int64_t ld, int64_t col0, int tr,
-              spx_state *st, const double *__restrict__ colbuf,
-              int32_t *__restrict__ rowlab, int32_t *__restrict__ collab,
-              int32_t *__restrict__ trace) {
+// One output pair of row i (global row index), generic: handles the pivot row (:155-156),
+// the pivot column (:159-160), the pivot cell (:163) and ordinary cells (:166-175).
+// jc = 0/1 when this thread's .x/.y is the pivot column, -1 otherwise.
+__device__ __forceinline__ double2 generic_pair(double2 t, int i, int r, int jc, double2 rj, double ci,
+                                                const PivotDiv &d) {
+    double2 o;
+    if (i == r) {
+        o.x = pivot_div(-t.x, d);
+        o.y = pivot_div(-t.y, d);
+        if (jc == 0) o.x = pivot_cell_update(d.p);
+        if (jc == 1) o.y = pivot_cell_update(d.p);
+    } else {
+        o.x = cell_update(t.x, d, rj.x, ci);
+        o.y = cell_update(t.y, d, rj.y, ci);
+        if (jc == 0) o.x = pivot_div(ci, d);
+        if (jc == 1) o.y = pivot_div(ci, d);
+    }
+    return o;
+}
+
+// the '-b' column (replicated when column-sharded) for rows [row_begin, row_end) + hint
+__device__ __forceinline__ void update_b_rows(const double *__restrict__ bin, double *__restrict__ bout,
+                                              const double *__restrict__ colbuf, int n, int r,
+                                              const PivotDiv &d, int i, bool valid, int *hint) {
+    int bneg = SPX_NONE;
+    if (valid && i < n) {
+        const double bi = bin[i];
+        const double nb = (i == r) ? pivot_div(-bi, d) : cell_update(bi, d, bin[r], colbuf[i]);
+        bout[i] = nb;
+        if (nb < 0.0) bneg = i;
+    }
+    const int w = __reduce_min_sync(0xffffffffu, bneg);
+    if ((threadIdx.x & 31) == 0 && w != SPX_NONE) atomicMin(hint, w);
+}
+
+// commit: labels (:152), trace, pivot counter — one thread of one CTA
+__device__ __forceinline__ void commit_pivot(spx_state *st, int r, int64_t cg, int slot,
+                                             int32_t *rowlab, int32_t *collab, int32_t *trace) {
+    const int64_t k = st->npiv;
+    const int32_t tmp = rowlab[cg]; rowlab[cg] = collab[r]; collab[r] = tmp;
+    if (trace) { trace[2 * k] = r; trace[2 * k + 1] = (int32_t)cg; }
+    st->hint_tag[slot] = k + 1;
+    st->npiv = k + 1;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(UPD_THREADS, MINB)
+update_tiled_kernel(const double *__restrict__ Ain, double *__restrict__ Aout,
+                    const double *__restrict__ bin, double *__restrict__ bout,
+                    int n, int m_loc, int64_t ld, int64_t col0, int tr,
+                    spx_state *st, const double *__restrict__ colbuf,
+                    int32_t *__restrict__ rowlab, int32_t *__restrict__ collab,
+                    int32_t *__restrict__ trace) {
     if (st->status != SPX_PIVOT) return;
 
     __shared__ alignas(128) double s_row[UPD_TC];
@@ -46,8 +103,8 @@ update_kernel(const double *__restrict__ Ain, double *__restrict__ Aout,
 
     const int     r    = st->r;
     const int64_t cg   = st->c;
-    const double  p    = st->p;
     const int     slot = st->slot;
+    const PivotDiv d   = pivot_div_prepare(st->p);
 
     const int tid  = threadIdx.x;
     const int j0   = blockIdx.x * UPD_TC;
@@ -69,74 +126,243 @@ update_kernel(const double *__restrict__ Ain, double *__restrict__ Aout,
 
     const int  j      = j0 + 2 * tid;                    // local column of .x
     const bool active = j < m_loc;
-    // column c inside this tile?  jc = 0/1 -> this thread's .x/.y is the pivot column
     const int64_t cl   = cg - col0;                      // local index of the pivot column
     const bool has_c   = (cl >= j0) && (cl < j0 + UPD_TC);
     const int  jc      = has_c ? (int)(cl - j) : -1;
+    const bool has_r   = (r >= i0) && (r < i0 + rows);
+    const bool has_f   = (i0 + rows == n + 1);
+    // CTA-uniform: interior tiles (no pivot row / pivot column / f row, full height)
+    const bool plain   = !has_c && !has_r && !has_f && (rows % UPD_UNROLL == 0);
 
     int fneg = SPX_NONE;                                 // first negative new f index in this thread
     if (active) {
         const double2 rj = *reinterpret_cast<const double2 *>(&s_row[2 * tid]);
         const double *src = Ain + (int64_t)i0 * ld + j;
         double *dst = Aout + (int64_t)i0 * ld + j;
-        for (int ii = 0; ii < rows; ii += UPD_UNROLL) {
-            double2 t[UPD_UNROLL];
+        if (plain) {
+            for (int ii = 0; ii < rows; ii += UPD_UNROLL) {
+                double2 t[UPD_UNROLL];
 #pragma unroll
-            for (int u = 0; u < UPD_UNROLL; ++u)
-                if (ii + u < rows) t[u] = ld_stream(src + (int64_t)(ii + u) * ld);
+                for (int u = 0; u < UPD_UNROLL; ++u) t[u] = ld_stream(src + (int64_t)(ii + u) * ld);
 #pragma unroll
-            for (int u = 0; u < UPD_UNROLL; ++u) {
-                if (ii + u < rows) {
-                    const int i = i0 + ii + u;
+                for (int u = 0; u < UPD_UNROLL; ++u) {
+                    const double ci = s_col[ii + u];
                     double2 o;
-                    if (i == r) {                                        // :155-156
-                        o.x = pivot_row_update(t[u].x, p);
-                        o.y = pivot_row_update(t[u].y, p);
-                        if (jc == 0) o.x = pivot_cell_update(p);         // :163
-                        if (jc == 1) o.y = pivot_cell_update(p);
-                    } else {                                             // :166-175
-                        const double ci = s_col[ii + u];
-                        o.x = cell_update(t[u].x, p, rj.x, ci);
-                        o.y = cell_update(t[u].y, p, rj.y, ci);
-                        if (jc == 0) o.x = pivot_col_update(ci, p);      // :159-160
-                        if (jc == 1) o.y = pivot_col_update(ci, p);
-                    }
+                    o.x = cell_update(t[u].x, d, rj.x, ci);
+                    o.y = cell_update(t[u].y, d, rj.y, ci);
                     st_stream(dst + (int64_t)(ii + u) * ld, o);
-                    if (i == n) {                                        // new f row: price the next pivot
-                        if (o.x < 0.0) fneg = j;
-                        else if (o.y < 0.0 && j + 1 < m_loc) fneg = j + 1;
+                }
+            }
+        } else {
+            for (int ii = 0; ii < rows; ii += UPD_UNROLL) {
+                double2 t[UPD_UNROLL];
+#pragma unroll
+                for (int u = 0; u < UPD_UNROLL; ++u)
+                    if (ii + u < rows) t[u] = ld_stream(src + (int64_t)(ii + u) * ld);
+#pragma unroll
+                for (int u = 0; u < UPD_UNROLL; ++u) {
+                    if (ii + u < rows) {
+                        const int i = i0 + ii + u;
+                        const double2 o = generic_pair(t[u], i, r, jc, rj, s_col[ii + u], d);
+                        st_stream(dst + (int64_t)(ii + u) * ld, o);
+                        if (i == n) {                                    // new f row: price the next pivot
+                            if (o.x < 0.0) fneg = j;
+                            else if (o.y < 0.0 && j + 1 < m_loc) fneg = j + 1;
+                        }
                     }
                 }
             }
         }
     }
-    if (i0 + rows == n + 1) {                            // this tile holds the f row (CTA-uniform)
+    if (has_f) {                                         // this tile holds the f row (CTA-uniform)
         const int w = __reduce_min_sync(0xffffffffu, fneg);
         if ((tid & 31) == 0 && w != SPX_NONE) atomicMin(&st->hint_fneg[slot], w);
     }
 
-    // ---- the '-b' column (replicated when column-sharded): column tile 0 does it
+    // ---- the '-b' column: column tile 0 does it
     if (blockIdx.x == 0) {
-        int bneg = SPX_NONE;
-        if (tid < rows && i0 + tid < n) {
-            const int i = i0 + tid;
-            const double bi = bin[i];
-            const double nb = (i == r) ? pivot_row_update(bi, p)
-                                       : cell_update(bi, p, bin[r], s_col[tid]);
-            bout[i] = nb;
-            if (nb < 0.0) bneg = i;
+        if (tid < 64)                                    // warps 0,1 cover tr <= 64 rows
+            update_b_rows(bin, bout, colbuf, n, r, d, i0 + tid, tid < rows, &st->hint_bneg[slot]);
+        if (blockIdx.y == 0 && tid == 0) commit_pivot(st, r, cg, slot, rowlab, collab, trace);
+    }
+}
+
+// ---- persistent TMA-pipelined kernel --------------------------------------------
+constexpr int PIPE_CONSUMERS = 256;                    // 8 consumer warps
+constexpr int PIPE_THREADS   = PIPE_CONSUMERS + 32;    // + 1 producer warp
+constexpr int PIPE_TC        = 2 * PIPE_CONSUMERS;     // 512 columns per tile
+constexpr int PIPE_TR        = 8;                      // rows per tile / stage
+constexpr int PIPE_STAGES    = 6;
+
+struct alignas(128) PipeStage {
+    double body[PIPE_TR][PIPE_TC];   // 32 KB
+    double row[PIPE_TC];             // pivot-row slice (valid when the column tile changed)
+    double col[16];                  // pivot-column slice of the tile's rows
+};
+constexpr size_t PIPE_SMEM = PIPE_STAGES * sizeof(PipeStage) + 2 * PIPE_STAGES * sizeof(uint64_t);
+
+struct TileIter {
+    // order 0: contiguous chunk per CTA, column tile major (pivot-row slice reloaded rarely)
+    // order 1: interleaved, row-tile major (neighbouring CTAs read neighbouring 4 KB pieces)
+    int64_t t, t_end, step;
+    int n_ct, n_rt, order;
+    __device__ __forceinline__ bool valid() const { return t < t_end; }
+    __device__ __forceinline__ void next() { t += step; }
+    __device__ __forceinline__ int ct() const { return order == 0 ? (int)(t / n_rt) : (int)(t % n_ct); }
+    __device__ __forceinline__ int rt() const { return order == 0 ? (int)(t % n_rt) : (int)(t / n_ct); }
+};
+
+__device__ __forceinline__ TileIter make_iter(int n_ct, int n_rt, int order) {
+    TileIter it;
+    it.n_ct = n_ct; it.n_rt = n_rt; it.order = order;
+    const int64_t total = (int64_t)n_ct * n_rt;
+    if (order == 0) {
+        const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+        it.t = (int64_t)blockIdx.x * per;
+        it.t_end = min(total, it.t + per);
+        it.step = 1;
+    } else {
+        it.t = blockIdx.x; it.t_end = total; it.step = gridDim.x;
+    }
+    return it;
+}
+
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+update_pipelined_kernel(const double *__restrict__ Ain, double *__restrict__ Aout,
+                        const double *__restrict__ bin, double *__restrict__ bout,
+                        int n, int m_loc, int64_t ld, int64_t col0, int order,
+                        spx_state *st, const double *__restrict__ colbuf,
+                        int32_t *__restrict__ rowlab, int32_t *__restrict__ collab,
+                        int32_t *__restrict__ trace) {
+    if (st->status != SPX_PIVOT) return;
+
+    extern __shared__ __align__(128) unsigned char pipe_smem[];
+    PipeStage *stg  = reinterpret_cast<PipeStage *>(pipe_smem);
+    uint64_t *full  = reinterpret_cast<uint64_t *>(pipe_smem + PIPE_STAGES * sizeof(PipeStage));
+    uint64_t *empty = full + PIPE_STAGES;
+
+    const int     r    = st->r;
+    const int64_t cg   = st->c;
+    const int     slot = st->slot;
+    const double  p    = st->p;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < PIPE_STAGES; ++s) {
+            mbar_init(&full[s], 1);                          // the producer's expect_tx arrive
+            mbar_init(&empty[s], PIPE_CONSUMERS / 32);       // one arrive per consumer warp
         }
-        if (tid < 64) {                                  // warps 0,1 cover tr <= 64 rows
-            const int w = __reduce_min_sync(0xffffffffu, bneg);
-            if ((tid & 31) == 0 && w != SPX_NONE) atomicMin(&st->hint_bneg[slot], w);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int n_ct = (m_loc + PIPE_TC - 1) / PIPE_TC;
+    const int n_rt = (n + 1 + PIPE_TR - 1) / PIPE_TR;
+    TileIter it = make_iter(n_ct, n_rt, order);
+
+    if (warp == PIPE_CONSUMERS / 32) {
+        // ---------------- producer warp: lane u < 8 copies row u of the tile, lane 8 the
+        // pivot-column slice, lane 9 the pivot-row slice; lane 0 posts the byte count
+        int prev_ct = -1;
+        for (int k = 0; it.valid(); it.next(), ++k) {
+            const int s = k % PIPE_STAGES;
+            const int use = k / PIPE_STAGES;
+            if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
+            const int ct = it.ct(), rt = it.rt();
+            const int j0 = ct * PIPE_TC, i0 = rt * PIPE_TR;
+            const int rows = min(PIPE_TR, n + 1 - i0);
+            const uint32_t row_bytes = (uint32_t)(min((int64_t)PIPE_TC, ld - j0) * 8);
+            const bool new_ct = (ct != prev_ct);
+            if (lane == 0)
+                mbar_expect_tx(&full[s], rows * row_bytes + PIPE_TR * 8 + (new_ct ? row_bytes : 0u));
+            if (lane < rows)
+                bulk_g2s(stg[s].body[lane], Ain + (int64_t)(i0 + lane) * ld + j0, row_bytes, &full[s]);
+            else if (lane == PIPE_TR)
+                bulk_g2s(stg[s].col, colbuf + i0, PIPE_TR * 8, &full[s]);
+            else if (lane == PIPE_TR + 1 && new_ct)
+                bulk_g2s(stg[s].row, Ain + (int64_t)r * ld + j0, row_bytes, &full[s]);
+            prev_ct = ct;
         }
-        // ---- commit: labels (:152), trace, pivot counter — one thread of one CTA
-        if (blockIdx.y == 0 && tid == 0) {
-            const int64_t k = st->npiv;
-            const int32_t tmp = rowlab[cg]; rowlab[cg] = collab[r]; collab[r] = tmp;
-            if (trace) { trace[2 * k] = r; trace[2 * k + 1] = (int32_t)cg; }
-            st->hint_tag[slot] = k + 1;
-            st->npiv = k + 1;
+        return;
+    }
+
+    // ---------------- consumers
+    const PivotDiv d = pivot_div_prepare(p);
+    const int64_t cl = cg - col0;
+    int prev_ct = -1;
+    double2 rj = make_double2(0.0, 0.0);
+    int fneg = SPX_NONE;
+    bool saw_f = false;
+    for (int k = 0; it.valid(); it.next(), ++k) {
+        const int s = k % PIPE_STAGES;
+        const int ct = it.ct(), rt = it.rt();
+        const int j0 = ct * PIPE_TC, i0 = rt * PIPE_TR;
+        const int rows = min(PIPE_TR, n + 1 - i0);
+        mbar_wait(&full[s], (uint32_t)((k / PIPE_STAGES) & 1));
+        if (ct != prev_ct) { rj = *reinterpret_cast<const double2 *>(&stg[s].row[2 * tid]); prev_ct = ct; }
+        double2 t[PIPE_TR];
+        double  ci[PIPE_TR];
+#pragma unroll
+        for (int u = 0; u < PIPE_TR; ++u) {
+            t[u]  = *reinterpret_cast<const double2 *>(&stg[s].body[u][2 * tid]);
+            ci[u] = stg[s].col[u];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);             // stage is in registers: release it
+
+        const int  j      = j0 + 2 * tid;
+        const bool active = j < m_loc;
+        const bool has_c  = (cl >= j0) && (cl < j0 + PIPE_TC);
+        const bool has_r  = (r >= i0) && (r < i0 + rows);
+        const bool has_f  = (i0 + rows == n + 1);
+        double *dst = Aout + (int64_t)i0 * ld + j;
+        if (!active) continue;                              // (never diverges inside a warp's barrier use)
+        if (!has_c && !has_r && !has_f) {                   // interior tile, full height
+#pragma unroll
+            for (int u = 0; u < PIPE_TR; ++u) {
+                double2 o;
+                o.x = cell_update(t[u].x, d, rj.x, ci[u]);
+                o.y = cell_update(t[u].y, d, rj.y, ci[u]);
+                st_stream(dst + (int64_t)u * ld, o);
+            }
+        } else {
+            const int jc = has_c ? (int)(cl - j) : -1;
+#pragma unroll
+            for (int u = 0; u < PIPE_TR; ++u) {
+                if (u < rows) {
+                    const int i = i0 + u;
+                    const double2 o = generic_pair(t[u], i, r, jc, rj, ci[u], d);
+                    st_stream(dst + (int64_t)u * ld, o);
+                    if (i == n) {
+                        saw_f = true;
+                        if (o.x < 0.0) fneg = min(fneg, j);
+                        else if (o.y < 0.0 && j + 1 < m_loc) fneg = min(fneg, j + 1);
+                    }
+                }
+            }
+        }
+    }
+    if (saw_f && fneg != SPX_NONE) atomicMin(&st->hint_fneg[slot], fneg);
+
+    // ---- the '-b' column, spread over the consumer threads of all CTAs
+    for (int base = blockIdx.x * PIPE_CONSUMERS; base < n; base += gridDim.x * PIPE_CONSUMERS)
+        update_b_rows(bin, bout, colbuf, n, r, d, base + tid, true, &st->hint_bneg[slot]);
+    if (blockIdx.x == 0 && tid == 0) commit_pivot(st, r, cg, slot, rowlab, collab, trace);
+}
+
+// a / p for arrays: the self-test of pivot_div against the compiler's div.rn.f64
+__global__ void division_selftest_kernel(const double *__restrict__ a, const double *__restrict__ p,
+                                         int64_t count, int64_t np, unsigned long long *mismatches,
+                                         double *first_bad) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        const double pv = p[k % np];
+        const PivotDiv d = pivot_div_prepare(pv);
+        const double q = pivot_div(a[k], d);
+        const double e = __ddiv_rn(a[k], pv);
+        const bool same = (__double_as_longlong(q) == __double_as_longlong(e)) || (q != q && e != e);
+        if (!same) {
+            if (atomicAdd(mismatches, 1ull) == 0ull) { first_bad[0] = a[k]; first_bad[1] = pv; }
         }
     }
 }
@@ -210,14 +436,67 @@ static int pick_tr(int n, int m_loc) {
     return tr;
 }
 
+// process-wide tuning knobs (spx_set_option); every setting computes the same bits
+int64_t g_opt[8] = {0, 0, 3, 0, 0, 0, 0, 0};
+
+int64_t get_option(int key) { return (key >= 0 && key < 8) ? g_opt[key] : -1; }
+int set_option(int key, int64_t value) {
+    switch (key) {
+    case SPX_OPT_UPDATE_KERNEL:    if (value < 0 || value > 2) return -1; break;
+    case SPX_OPT_TILED_MIN_BLOCKS: if (value < 1 || value > 4) return -1; break;
+    case SPX_OPT_PIPE_ORDER:       if (value < 0 || value > 1) return -1; break;
+    case SPX_OPT_PIPE_GRID:        if (value < 0 || value > 4096) return -1; break;
+    default: return -1;
+    }
+    g_opt[key] = value;
+    return 0;
+}
+
 cudaError_t update(const double *Ain, double *Aout, const double *bin, double *bout, int n,
                    int m_loc, int64_t ld, int64_t col0, spx_state *st, const double *colbuf,
                    int32_t *rowlab, int32_t *collab, int32_t *trace, cudaStream_t stream) {
+    int kernel = (int)g_opt[SPX_OPT_UPDATE_KERNEL];
+    // measured on B200 (profiles/): the tiled kernel streams at the copy rate already; the
+    // pipelined kernel stays selectable for experiments
+    if (kernel == 0) kernel = 1;
+    if (kernel == 2) {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(update_pipelined_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        const int64_t tiles = (((int64_t)m_loc + PIPE_TC - 1) / PIPE_TC) * (((int64_t)n + 1 + PIPE_TR - 1) / PIPE_TR);
+        int64_t grid = g_opt[SPX_OPT_PIPE_GRID] > 0 ? g_opt[SPX_OPT_PIPE_GRID] : sm_count();
+        if (tiles < grid) grid = tiles;
+        if (grid < 1) grid = 1;                       // a shard with no columns still updates b
+        update_pipelined_kernel<<<(unsigned)grid, PIPE_THREADS, PIPE_SMEM, stream>>>(
+            Ain, Aout, bin, bout, n, m_loc, ld, col0, (int)g_opt[SPX_OPT_PIPE_ORDER], st, colbuf,
+            rowlab, collab, trace);
+        spx_host::count_launch();
+        return cudaGetLastError();
+    }
     const int tr = pick_tr(n, m_loc);
     dim3 grid((unsigned)((m_loc + UPD_TC - 1) / UPD_TC), (unsigned)((n + 1 + tr - 1) / tr));
     if (grid.x == 0) grid.x = 1;      // a shard with no columns still updates b
-    update_kernel<<<grid, UPD_THREADS, 0, stream>>>(Ain, Aout, bin, bout, n, m_loc, ld, col0, tr,
-                                                    st, colbuf, rowlab, collab, trace);
+#define SPX_LAUNCH_TILED(MINB)                                                                      \
+    update_tiled_kernel<MINB><<<grid, UPD_THREADS, 0, stream>>>(Ain, Aout, bin, bout, n, m_loc, ld, \
+                                                               col0, tr, st, colbuf, rowlab, collab, trace)
+    switch ((int)g_opt[SPX_OPT_TILED_MIN_BLOCKS]) {
+    case 1: SPX_LAUNCH_TILED(1); break;
+    case 2: SPX_LAUNCH_TILED(2); break;
+    case 4: SPX_LAUNCH_TILED(4); break;
+    default: SPX_LAUNCH_TILED(3); break;
+    }
+#undef SPX_LAUNCH_TILED
+    spx_host::count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t selftest_division(const double *a, const double *p, int64_t count, int64_t np,
+                              unsigned long long *d_mismatches, double *d_first_bad, cudaStream_t stream) {
+    division_selftest_kernel<<<sm_count() * 8, 256, 0, stream>>>(a, p, count, np, d_mismatches, d_first_bad);
     spx_host::count_launch();
     return cudaGetLastError();
 }

@@ -232,6 +232,79 @@ def test_ratio_scan_special_values(spx):
         assert (both_nan | (bits(res.tables[0]) == bits(o.table))).all()
 
 
+# --------------------------------------------------------------------------- K3 internals
+def test_hoisted_reciprocal_division_equals_div_rn(spx):
+    """pivot_div (reciprocal hoisted out of the cell loop) == the compiler's div.rn.f64, bit for bit."""
+    import ctypes
+    torch = spx.torch
+    L = spx.N.lib()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cnt = 1 << 24
+
+    def bits(lo_exp, hi_exp, count):
+        mant = torch.randint(0, 1 << 52, (count,), generator=g, device="cuda", dtype=torch.int64)
+        exp = torch.randint(lo_exp, hi_exp + 1, (count,), generator=g, device="cuda", dtype=torch.int64)
+        sign = torch.randint(0, 2, (count,), generator=g, device="cuda", dtype=torch.int64) << 63
+        return (mant | (exp << 52) | sign).view(torch.float64)
+
+    specials = torch.tensor([0.0, -0.0, 1.0, -1.0, float("inf"), -float("inf"), float("nan"), 5e-324, -5e-324,
+                             2.2250738585072014e-308, 1.7976931348623157e308, 1e-300, 1e300, 3.0, 1.0 / 3.0,
+                             0.9954454131449921, 2.0 ** -969, 2.0 ** -970, 2.0 ** 1017, 2.0 ** 1016],
+                            dtype=torch.float64, device="cuda")
+    suites = [
+        (bits(1023 - 40, 1023 + 40, cnt), bits(1023 - 40, 1023 + 40, 4096)),      # ordinary tableau magnitudes
+        (bits(0, 2046, cnt), bits(0, 2046, 4096)),                                # whole exponent range + denormals
+        (bits(1, 120, cnt), bits(900, 1100, 1024)),                               # tiny numerators (guard 1)
+        (bits(1000, 1046, cnt), bits(1, 60, 1024)),                               # overflowing quotients
+        (bits(1, 80, cnt), bits(1980, 2046, 1024)),                               # underflowing quotients / huge p
+        (specials.repeat_interleave(specials.numel()), specials),                 # specials x specials
+    ]
+    # near-midpoint quotients: a = q*p rounded, with q having a long run of 1s / 0s at the bottom
+    q = (bits(1023, 1023, cnt).view(torch.int64) | 0x7FF).view(torch.float64)
+    pp = bits(1023, 1023, 4096)
+    suites.append((q * pp[torch.arange(cnt, device="cuda") % 4096], pp))
+    for a, p in suites:
+        a = a.contiguous(); p = p.contiguous()
+        bad = ctypes.c_uint64(123)
+        first = (ctypes.c_double * 2)()
+        rc = L.spx_selftest_division(a.data_ptr(), p.data_ptr(), a.numel(), p.numel(), ctypes.byref(bad), first,
+                                     torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        assert bad.value == 0, (bad.value, first[0].hex(), first[1].hex())
+
+
+@pytest.mark.parametrize("opts", [{1: 1, 2: 2}, {1: 1, 2: 3}, {1: 1, 2: 4}, {1: 2, 3: 0}, {1: 2, 3: 1},
+                                  {1: 2, 3: 0, 4: 7}, {1: 2, 3: 1, 4: 5}])
+def test_every_update_kernel_variant_is_bit_exact(spx, opts):
+    """Tiled (every register budget) and TMA-pipelined (both tile orders, odd grids) update kernels
+    against the oracle on ragged shapes, including tiles with the pivot row/column and the f row."""
+    L = spx.N.lib()
+    try:
+        for k, v in opts.items():
+            assert L.spx_set_option(k, v) == 0
+        for n, m in [(1, 2), (7, 15), (9, 17), (64, 512), (65, 513), (130, 1030), (40, 2049), (300, 700)]:
+            rng = np.random.default_rng(n * 77 + m)
+            rows, c = W.dense_lp(n, m, seed=n + m)
+            rows[rng.random(rows.shape) < 0.05] = 0.0
+            dev = spx.engine.DeviceTableau(n, m, trace_capacity=16)
+            dev.load(rows, c, max_pivots=16)
+            T = flat_of(rows, c)
+            for npiv in range(6):
+                st, r, cc, e = oracle.pick(T, n, m)
+                dev.pick(npiv)
+                s = dev.read_state()
+                assert s.status == st
+                if st != oracle.PIVOT:
+                    break
+                assert (s.r, s.c, s.p) == (r, cc, e)
+                dev.update(npiv)
+                T = oracle.update(T, n, m, r, cc)
+                assert np.array_equal(bits(dev.export_flat(npiv + 1)), bits(T)), (opts, n, m, npiv)
+    finally:
+        for k, v in {1: 0, 2: 3, 3: 0, 4: 0}.items():
+            L.spx_set_option(k, v)
+
+
 # --------------------------------------------------------------------------- BASELINE configs
 def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests):
     g = cfg_digests["cfg2"]
