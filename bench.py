@@ -239,8 +239,8 @@ def run_ours(args):
 
     if world == 1:
         # ---------------- value: tableau resident in HBM --------------------------------
-        tab = DeviceTableau(N_ROWS, M_COLS, device=dev, trace_capacity=need)
-        tab.load(rows, c, max_pivots=need)
+        tab = DeviceTableau(N_ROWS, M_COLS, device=dev, trace_capacity=need + 64)
+        tab.load(rows, c, max_pivots=need + 64)   # the cap is never reached inside the timed region
         for _ in range(args.warmup):
             st, npiv = tab.solve(chunk=P, stop_after=P)
         torch.cuda.synchronize()
@@ -336,8 +336,8 @@ def run_ours(args):
 
     # ---------------- N > 1: column-sharded, one process per GPU ---------------------------
     from simplex_method_solver_b200.parallel import ShardedTableau
-    sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need)
-    sh.load(rows, c, max_pivots=need)
+    sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
+    sh.load(rows, c, max_pivots=need + 64)
     del rows
     for _ in range(args.warmup):
         sh.run(P)

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define SPX_ABI_VERSION 1
+#define SPX_ABI_VERSION 2
 
 /* status codes == the outcomes of pick_element(), simplex.py:70-141 */
 #define SPX_PIVOT       1   /* (True, r, c, e)                                   :91,:141 */
@@ -146,13 +146,24 @@ int spx_update(const double *d_Ain, double *d_Aout, const double *d_bin, double 
  * table is in buffer (npiv & 1) where npiv is read from d_state.  Enqueues
  * pick+update pairs in chunks of `chunk` pivots with no host round trip, then
  * reads the state back; stops on a terminal status, at d_state->max_pivots
- * (SPX_CAP), or after `stop_after` further pivots (status stays SPX_PIVOT;
- * <= 0: no such limit).  d_trace is [max_pivots][2] int32 or NULL.
- * On return *h_status / *h_npiv mirror d_state. */
+ * (SPX_CAP), or after `stop_after` further pivots (<= 0: no such limit; the status is
+ * then SPX_PIVOT in classic mode and, in look-ahead mode, the already priced outcome of
+ * the current table — SPX_PIVOT, or its terminal status).  d_trace is [max_pivots][2] int32 or NULL.
+ * On return *h_status / *h_npiv mirror d_state.
+ *
+ * d_work == NULL: classic order pick k, update k, pick k+1, ... on `stream`.
+ * d_work != NULL (128-byte aligned, >= spx_solve_workspace_bytes(n)): LOOK-AHEAD.  While the
+ * streaming update of pivot k runs on `stream`, a high-priority side stream owned by the
+ * library prices pivot k+1 from the same (old) table — the next b column, the next f /
+ * phase-1 row and the next entering column are O(n+m) cells computed with the update's own
+ * arithmetic — so the update kernels run back to back and pricing is off the critical path.
+ * Pivot sequence and every cell are identical in both modes. */
+int64_t spx_solve_workspace_bytes(int32_t n);
 int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1,
               int32_t n, int32_t m, int64_t ld, int32_t rule,
               spx_state *d_state, double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab,
               int32_t *d_trace, int32_t chunk, int64_t stop_after,
+              void *d_work, int64_t work_bytes,
               int32_t *h_status, int64_t *h_npiv, void *stream);
 
 /* ---- find_optimum() / f(), simplex.py:48-68, generalised to m variables --- */
@@ -197,10 +208,30 @@ int spx_shard_candidate(const double *d_A, const double *d_b, int32_t n, int32_t
 int spx_shard_select(const double *d_gathered, int32_t nranks, const double *d_b,
                      int32_t n, int32_t rule, int32_t sticky, spx_state *d_state,
                      double *d_colbuf, void *stream);
+/* ahead != 0: look-ahead mode — the kernel only reads *d_state, skips the b column and the
+ * pricing hints (spx_ahead_candidate / spx_ahead_select own them) and still swaps the labels
+ * and appends to the trace. */
 int spx_shard_update(const double *d_Ain, double *d_Aout, const double *d_bin, double *d_bout,
                      int32_t n, int32_t m_loc, int64_t ld_loc, int64_t col0,
                      spx_state *d_state, const double *d_colbuf,
-                     int32_t *d_rowlab, int32_t *d_collab, int32_t *d_trace, void *stream);
+                     int32_t *d_rowlab, int32_t *d_collab, int32_t *d_trace,
+                     int32_t ahead, void *stream);
+
+/* Look-ahead halves of the sharded flow: they price pivot k+1 from table k (the table the
+ * running update of pivot k reads), so they can run on another stream concurrently with it:
+ *   spx_ahead_candidate : next b column (d_bin -> d_bout, every rank), this shard's best
+ *                         entering column of the NEXT table and that column's n+1 next cells,
+ *                         packed into d_send (spx_shard_msg_doubles(n) doubles);
+ *   (all-gather of d_send)
+ *   spx_ahead_select    : min key over ranks + ratio test with the next b; writes the NEXT
+ *                         state (npiv+1) and colbuf, leaving the current ones untouched.
+ * Terminal states propagate: once *d_state_cur is not SPX_PIVOT the next state is a copy. */
+int spx_ahead_candidate(const double *d_A, const double *d_bin, double *d_bout, int32_t n, int32_t m_loc,
+                        int64_t ld_loc, int64_t col0, int32_t rule, const spx_state *d_state,
+                        const double *d_colbuf, double *d_send, void *stream);
+int spx_ahead_select(const double *d_gathered, int32_t nranks, const double *d_bnext, int32_t n,
+                     const spx_state *d_state_cur, spx_state *d_state_next, double *d_colbuf_next,
+                     void *stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libspx_b200.so")
 
+ABI_VERSION = 2
 PIVOT, OPTIMAL, INCORRECT, NOCONV, CAP = 1, 0, -1, -2, -3
 RULE_REFERENCE, RULE_DANTZIG = 0, 1
 OPT_UPDATE_KERNEL, OPT_TILED_MIN_BLOCKS, OPT_PIPE_ORDER, OPT_PIPE_GRID = 1, 2, 3, 4
@@ -65,8 +66,9 @@ SIGNATURES = {
     "spx_init_state": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp]),
     "spx_pick": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     "spx_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "spx_solve_workspace_bytes": (_i64, [_i32]),
     "spx_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
-                                 _i32, _i64, _pi32, _pi64, _vp]),
+                                 _i32, _i64, _vp, _i64, _pi32, _pi64, _vp]),
     "spx_extract": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "spx_solve_batched": (ctypes.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                          _vp, _vp, _vp]),
@@ -75,7 +77,9 @@ SIGNATURES = {
     "spx_shard_candidate": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     "spx_shard_select": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "spx_shard_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp,
-                                        _vp, _vp]),
+                                        _vp, _i32, _vp]),
+    "spx_ahead_candidate": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "spx_ahead_select": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -95,7 +99,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(L, name)           # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
-    if L.spx_version() != 1:
+    if L.spx_version() != ABI_VERSION:
         raise NativeUnavailable("libspx_b200.so ABI version mismatch")
     if L.spx_state_bytes() != ctypes.sizeof(SpxState):
         raise NativeUnavailable("spx_state layout mismatch between header and Python mirror")

@@ -21,7 +21,11 @@ cudaError_t shard_candidate(const double *, const double *, int, int, int64_t, i
 cudaError_t shard_select(const double *, int, const double *, int, int, spx_state *, double *,
                          cudaStream_t);
 cudaError_t update(const double *, double *, const double *, double *, int, int, int64_t, int64_t,
-                   spx_state *, const double *, int32_t *, int32_t *, int32_t *, cudaStream_t);
+                   spx_state *, const double *, int32_t *, int32_t *, int32_t *, int, cudaStream_t);
+cudaError_t ahead_candidate(const double *, const double *, double *, int, int, int64_t, int64_t, int,
+                            const spx_state *, const double *, double *, cudaStream_t);
+cudaError_t ahead_select(const double *, int, const double *, int, const spx_state *, spx_state *,
+                         double *, cudaStream_t);
 cudaError_t extract(const double *, int, int, const int32_t *, const double *, double *, double *,
                     cudaStream_t);
 int64_t get_option(int);
@@ -219,33 +223,84 @@ int spx_pick(const double *d_A, const double *d_b, int32_t n, int32_t m, int64_t
 int spx_shard_update(const double *d_Ain, double *d_Aout, const double *d_bin, double *d_bout,
                      int32_t n, int32_t m_loc, int64_t ld_loc, int64_t col0, spx_state *d_state,
                      const double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab, int32_t *d_trace,
-                     void *stream) {
+                     int32_t ahead, void *stream) {
     if (validate_split("spx_update", d_Ain, d_bin, n, m_loc, ld_loc)) return -2;
     if (validate_split("spx_update", d_Aout, d_bout, n, m_loc, ld_loc)) return -2;
     SPX_REQUIRE(d_Ain != d_Aout && d_bin != d_bout, "spx_update: the pivot is out of place; in == out");
     SPX_REQUIRE(d_state && d_colbuf && d_rowlab && d_collab, "spx_update: null state/colbuf/labels");
     SPX_REQUIRE(((uintptr_t)d_colbuf & 15) == 0, "spx_update: colbuf must be 16-byte aligned");
     return check(spx_launch::update(d_Ain, d_Aout, d_bin, d_bout, n, m_loc, ld_loc, col0, d_state, d_colbuf,
-                                    d_rowlab, d_collab, d_trace, as_stream(stream)), "update launch");
+                                    d_rowlab, d_collab, d_trace, ahead ? 1 : 0, as_stream(stream)),
+                 "update launch");
 }
 
 int spx_update(const double *d_Ain, double *d_Aout, const double *d_bin, double *d_bout, int32_t n,
                int32_t m, int64_t ld, spx_state *d_state, const double *d_colbuf, int32_t *d_rowlab,
                int32_t *d_collab, int32_t *d_trace, void *stream) {
     return spx_shard_update(d_Ain, d_Aout, d_bin, d_bout, n, m, ld, 0, d_state, d_colbuf, d_rowlab,
-                            d_collab, d_trace, stream);
+                            d_collab, d_trace, 0, stream);
 }
 
 // ---- the pivot loop -------------------------------------------------------------
+namespace {
+
+// look-ahead workspace: [second state | second colbuf | candidate message]
+struct Workspace {
+    spx_state *state2;
+    double    *colbuf2;
+    double    *msg;
+};
+inline int64_t align128(int64_t v) { return (v + 127) / 128 * 128; }
+int64_t workspace_bytes(int n) {
+    return align128(sizeof(spx_state)) + align128(spx_launch::colbuf_doubles(n) * 8) +
+           align128(spx_launch::shard_msg_doubles(n) * 8);
+}
+Workspace carve(void *base, int n) {
+    char *p = static_cast<char *>(base);
+    Workspace w;
+    w.state2 = reinterpret_cast<spx_state *>(p);  p += align128(sizeof(spx_state));
+    w.colbuf2 = reinterpret_cast<double *>(p);    p += align128(spx_launch::colbuf_doubles(n) * 8);
+    w.msg = reinterpret_cast<double *>(p);
+    return w;
+}
+
+// one high-priority side stream + fork/join events per device, created on first use
+struct SideCtx { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+SideCtx g_side[64];
+
+int side_ctx(SideCtx **out) {
+    int dev = 0;
+    if (check(cudaGetDevice(&dev), "cudaGetDevice")) return -1;
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return -1; }
+    SideCtx &c = g_side[dev];
+    if (!c.side) {
+        int lo = 0, hi = 0;
+        if (check(cudaDeviceGetStreamPriorityRange(&lo, &hi), "priority range")) return -1;
+        if (check(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi), "side stream")) return -1;
+        if (check(cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming), "event")) return -1;
+        if (check(cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming), "event")) return -1;
+    }
+    *out = &c;
+    return 0;
+}
+
+} // namespace
+
+int64_t spx_solve_workspace_bytes(int32_t n) { return workspace_bytes(n); }
+
 int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n, int32_t m, int64_t ld,
               int32_t rule, spx_state *d_state, double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab,
-              int32_t *d_trace, int32_t chunk, int64_t stop_after, int32_t *h_status, int64_t *h_npiv,
-              void *stream) {
+              int32_t *d_trace, int32_t chunk, int64_t stop_after, void *d_work, int64_t work_bytes,
+              int32_t *h_status, int64_t *h_npiv, void *stream) {
     if (validate_split("spx_solve", d_A0, d_b0, n, m, ld)) return -2;
     if (validate_split("spx_solve", d_A1, d_b1, n, m, ld)) return -2;
     SPX_REQUIRE(d_state && d_colbuf && d_rowlab && d_collab, "spx_solve: null state/colbuf/labels");
     SPX_REQUIRE(chunk >= 1, "spx_solve: chunk must be >= 1");
     SPX_REQUIRE(rule == SPX_RULE_REFERENCE || rule == SPX_RULE_DANTZIG, "spx_solve: unknown rule %d", rule);
+    const bool ahead = (d_work != nullptr);
+    SPX_REQUIRE(!ahead || (work_bytes >= workspace_bytes(n) && ((uintptr_t)d_work & 127) == 0),
+                "spx_solve: workspace must be 128-byte aligned and >= spx_solve_workspace_bytes(n) = %lld bytes",
+                (long long)workspace_bytes(n));
     cudaStream_t s = as_stream(stream);
     double *A[2] = {d_A0, d_A1};
     double *b[2] = {d_b0, d_b1};
@@ -257,25 +312,57 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
         if (check(cudaMemcpyAsync(&d_state->status, &run, sizeof(run), cudaMemcpyHostToDevice, s), "resume")) return -1;
         hs.status = SPX_PIVOT;
     }
+    SideCtx *sc = nullptr;
+    Workspace w{};
+    if (ahead) {
+        if (side_ctx(&sc)) return -1;
+        w = carve(d_work, n);
+    }
     int64_t done = 0;
+    bool priced = false;      // look-ahead: d_state/d_colbuf already hold the pick of the current table
     while (hs.status == SPX_PIVOT) {
         int64_t k = chunk;
         if (stop_after > 0 && stop_after - done < k) k = stop_after - done;
         if (k <= 0) break;
         const int64_t base = hs.npiv;
-        for (int64_t q = 0; q < k; ++q) {
-            const int cur = (int)((base + q) & 1);
-            if (check(spx_launch::pick(A[cur], b[cur], n, m, ld, rule, 1, d_state, d_colbuf, s), "pick launch")) return -1;
-            if (check(spx_launch::update(A[cur], A[cur ^ 1], b[cur], b[cur ^ 1], n, m, ld, 0, d_state, d_colbuf,
-                                         d_rowlab, d_collab, d_trace, s), "update launch")) return -1;
+        if (!ahead) {
+            // classic: pick k, update k, pick k+1, ... on one stream
+            for (int64_t q = 0; q < k; ++q) {
+                const int cur = (int)((base + q) & 1);
+                if (check(spx_launch::pick(A[cur], b[cur], n, m, ld, rule, 1, d_state, d_colbuf, s), "pick launch")) return -1;
+                if (check(spx_launch::update(A[cur], A[cur ^ 1], b[cur], b[cur ^ 1], n, m, ld, 0, d_state, d_colbuf,
+                                             d_rowlab, d_collab, d_trace, 0, s), "update launch")) return -1;
+            }
+        } else {
+            // look-ahead: while update q streams on `s`, the side stream prices pivot q+1 from the
+            // same (old) table into the other state/colbuf; the two join before update q+1
+            spx_state *S[2] = {d_state, w.state2};
+            double *C[2] = {d_colbuf, w.colbuf2};
+            if (!priced)
+                if (check(spx_launch::pick(A[base & 1], b[base & 1], n, m, ld, rule, 1, d_state, d_colbuf, s), "pick launch")) return -1;
+            for (int64_t q = 0; q < k; ++q) {
+                const int cur = (int)((base + q) & 1), si = (int)(q & 1);
+                if (check(cudaEventRecord(sc->fork, s), "fork")) return -1;
+                if (check(cudaStreamWaitEvent(sc->side, sc->fork, 0), "fork wait")) return -1;
+                if (check(spx_launch::ahead_candidate(A[cur], b[cur], b[cur ^ 1], n, m, ld, 0, rule, S[si], C[si],
+                                                      w.msg, sc->side), "candidate launch")) return -1;
+                if (check(spx_launch::ahead_select(w.msg, 1, b[cur ^ 1], n, S[si], S[si ^ 1], C[si ^ 1], sc->side),
+                          "select launch")) return -1;
+                if (check(cudaEventRecord(sc->join, sc->side), "join")) return -1;
+                if (check(spx_launch::update(A[cur], A[cur ^ 1], b[cur], b[cur ^ 1], n, m, ld, 0, S[si], C[si],
+                                             d_rowlab, d_collab, d_trace, 1, s), "update launch")) return -1;
+                if (check(cudaStreamWaitEvent(s, sc->join, 0), "join wait")) return -1;
+            }
+            if (k & 1) {   // the newest state/column sit in the workspace: bring them home
+                if (check(cudaMemcpyAsync(d_state, w.state2, sizeof(spx_state), cudaMemcpyDeviceToDevice, s), "state copy")) return -1;
+                if (check(cudaMemcpyAsync(d_colbuf, w.colbuf2, (size_t)(n + 1) * sizeof(double),
+                                          cudaMemcpyDeviceToDevice, s), "colbuf copy")) return -1;
+            }
+            priced = true;
         }
         if (check(cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, s), "read state")) return -1;
         if (check(cudaStreamSynchronize(s), "pivot chunk")) return -1;
         done += k;
-        if (hs.status != SPX_PIVOT) break;
-    }
-    if (hs.status == SPX_PIVOT && !(stop_after > 0 && done >= stop_after)) {
-        // nothing enqueued (e.g. stop_after exhausted before the first chunk)
     }
     if (h_status) *h_status = hs.status;
     if (h_npiv) *h_npiv = hs.npiv;
@@ -328,6 +415,26 @@ int spx_shard_select(const double *d_gathered, int32_t nranks, const double *d_b
                 "spx_shard_select: bad arguments");
     return check(spx_launch::shard_select(d_gathered, nranks, d_b, n, sticky, d_state, d_colbuf,
                                           as_stream(stream)), "select launch");
+}
+
+int spx_ahead_candidate(const double *d_A, const double *d_bin, double *d_bout, int32_t n, int32_t m_loc,
+                        int64_t ld_loc, int64_t col0, int32_t rule, const spx_state *d_state,
+                        const double *d_colbuf, double *d_send, void *stream) {
+    if (validate_split("spx_ahead_candidate", d_A, d_bin, n, m_loc, ld_loc)) return -2;
+    SPX_REQUIRE(d_bout && d_bout != d_bin && d_state && d_colbuf && d_send && col0 >= 0,
+                "spx_ahead_candidate: bad arguments");
+    SPX_REQUIRE(rule == SPX_RULE_REFERENCE || rule == SPX_RULE_DANTZIG, "spx_ahead_candidate: unknown rule %d", rule);
+    return check(spx_launch::ahead_candidate(d_A, d_bin, d_bout, n, m_loc, ld_loc, col0, rule, d_state, d_colbuf,
+                                             d_send, as_stream(stream)), "candidate launch");
+}
+
+int spx_ahead_select(const double *d_gathered, int32_t nranks, const double *d_bnext, int32_t n,
+                     const spx_state *d_state_cur, spx_state *d_state_next, double *d_colbuf_next,
+                     void *stream) {
+    SPX_REQUIRE(d_gathered && d_bnext && d_state_cur && d_state_next && d_colbuf_next && nranks >= 1 && n >= 1 &&
+                d_state_cur != d_state_next, "spx_ahead_select: bad arguments");
+    return check(spx_launch::ahead_select(d_gathered, nranks, d_bnext, n, d_state_cur, d_state_next,
+                                          d_colbuf_next, as_stream(stream)), "select launch");
 }
 
 } // extern "C"

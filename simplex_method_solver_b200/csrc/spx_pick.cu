@@ -35,7 +35,7 @@ __device__ __forceinline__ int block_min_int(int v, Scratch &s) {
     if (lane == 0) s.red_i[warp] = v;
     __syncthreads();
     if (warp == 0) {
-        int w = warp_min_int(s.red_i[lane]);
+        int w = warp_min_int(lane < (int)(blockDim.x >> 5) ? s.red_i[lane] : SPX_NONE);
         if (lane == 0) s.out_i = w;
     }
     __syncthreads();
@@ -59,7 +59,7 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
     if (lane == 0) s.red_k[warp] = v;
     __syncthreads();
     if (warp == 0) {
-        unsigned long long w = warp_min_u64(s.red_k[lane]);
+        unsigned long long w = warp_min_u64(lane < (int)(blockDim.x >> 5) ? s.red_k[lane] : ~0ull);
         if (lane == 0) s.out_k = w;
     }
     __syncthreads();
@@ -74,7 +74,7 @@ __device__ __forceinline__ Ratio block_ratio_reduce(Ratio q, Scratch &s) {
     if (lane == 0) s.red_q[warp] = q;
     __syncthreads();
     if (warp == 0) {
-        Ratio w = warp_ratio_reduce(s.red_q[lane]);
+        Ratio w = warp_ratio_reduce(lane < (int)(blockDim.x >> 5) ? s.red_q[lane] : ratio_identity());
         if (lane == 0) s.out_q = w;
     }
     __syncthreads();
@@ -89,12 +89,31 @@ struct IsPos { __device__ bool operator()(double v) const { return v > 0.0; } };
 // first j in [0, len) with pred(x[j]); chunked so the usual early hit costs one pass
 template <class Pred>
 __device__ int block_first_index(const double *__restrict__ x, int len, Pred pred, Scratch &s) {
-    for (int base = 0; base < len; base += PICK_THREADS * 4) {
+    const int nt = (int)blockDim.x;
+    for (int base = 0; base < len; base += nt * 4) {
         int loc = SPX_NONE;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int j = base + u * PICK_THREADS + (int)threadIdx.x;
+            const int j = base + u * nt + (int)threadIdx.x;
             if (j < len && pred(x[j])) loc = min(loc, j);
+        }
+        loc = block_min_int(loc, s);
+        if (loc != SPX_NONE) return loc;
+    }
+    return SPX_NONE;
+}
+
+// same search over values produced on the fly: val(j) is the cell j of a row that does not
+// exist in memory yet (the look-ahead kernels price the NEXT table from the current one)
+template <class Val, class Pred>
+__device__ int block_first_index_fn(int len, Val val, Pred pred, Scratch &s) {
+    const int nt = (int)blockDim.x;
+    for (int base = 0; base < len; base += nt * 4) {
+        int loc = SPX_NONE;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = base + u * nt + (int)threadIdx.x;
+            if (j < len && pred(val(j))) loc = min(loc, j);
         }
         loc = block_min_int(loc, s);
         if (loc != SPX_NONE) return loc;
@@ -127,14 +146,14 @@ __device__ void block_entering(const double *__restrict__ A, const double *__res
     }
     // Dantzig: most negative f[j], lowest index on ties
     unsigned long long best = ~0ull;
-    for (int j = threadIdx.x; j < m_loc; j += PICK_THREADS) {
+    for (int j = threadIdx.x; j < m_loc; j += blockDim.x) {
         const double v = f[j];
         if (v < 0.0) { const unsigned long long k = orderable(v); best = k < best ? k : best; }
     }
     best = block_min_u64(best, s);
     if (best == ~0ull) { cloc = SPX_NONE; return; }
     int loc = SPX_NONE;
-    for (int j = threadIdx.x; j < m_loc; j += PICK_THREADS) {
+    for (int j = threadIdx.x; j < m_loc; j += blockDim.x) {
         const double v = f[j];
         if (v < 0.0 && orderable(v) == best) { loc = j; break; }
     }
@@ -142,46 +161,60 @@ __device__ void block_entering(const double *__restrict__ A, const double *__res
     keyhi = best;
 }
 
-// K2 + bookkeeping once the entering column is known.
+// K2 once the entering column is known: gathers the column into colbuf and runs the ratio
+// test; every thread returns the same decision.
 //   col/stride : where the winning column lives (tableau: stride ld; message: stride 1)
 //   r1         : phase-1 row or -1;  cglob : global column index or -1 (none)
+//   npiv/cap   : pivots applied to the table being priced / max_pivots
+struct Decision { int status; int r; double p; };
+
+__device__ Decision block_decide(const double *__restrict__ col, int64_t stride,
+                                 const double *__restrict__ b, int n, int r1, int64_t cglob,
+                                 int64_t npiv, int64_t cap, double *__restrict__ colbuf, Scratch &s) {
+    Decision dec; dec.r = -1; dec.p = 0.0;
+    if (cglob < 0) {
+        dec.status = (r1 >= 0) ? SPX_INCORRECT : SPX_OPTIMAL;          // :88-89, :101-103
+        return dec;
+    }
+    Ratio q = ratio_identity();
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) {
+        const double a = col[(int64_t)i * stride];
+        colbuf[i] = a;
+        if (r1 < 0 && i < n) ratio_accumulate(q, i, a, b[i]);          // :111-136
+    }
+    int r;
+    if (r1 >= 0) {
+        r = r1;                                                        // :91, no ratio test in phase 1
+    } else {
+        q = block_ratio_reduce(q, s);
+        bool elig_nan = false;
+        if (q.elig_row != SPX_NONE) {
+            const double v = __ddiv_rn(b[q.elig_row], col[(int64_t)q.elig_row * stride]);
+            elig_nan = (v != v);
+        }
+        r = ratio_decide(q, elig_nan);                                 // :138-141
+    }
+    dec.status = (r < 0) ? SPX_NOCONV : SPX_PIVOT;
+    if (dec.status == SPX_PIVOT) {
+        dec.r = r;
+        dec.p = col[(int64_t)r * stride];
+        if (npiv >= cap) dec.status = SPX_CAP;
+    }
+    return dec;
+}
+
+// in-place bookkeeping of the step API (spx_pick / spx_shard_select): the update that follows
+// increments npiv and fills the hint slot
 __device__ void block_finish(const double *__restrict__ col, int64_t stride,
                              const double *__restrict__ b, int n, int r1, int64_t cglob,
                              spx_state *st, double *__restrict__ colbuf, Scratch &s) {
-    int status, r = -1;
-    double p = 0.0;
-    if (cglob < 0) {
-        status = (r1 >= 0) ? SPX_INCORRECT : SPX_OPTIMAL;              // :88-89, :101-103
-    } else {
-        Ratio q = ratio_identity();
-        for (int i = threadIdx.x; i <= n; i += PICK_THREADS) {
-            const double a = col[(int64_t)i * stride];
-            colbuf[i] = a;
-            if (r1 < 0 && i < n) ratio_accumulate(q, i, a, b[i]);      // :111-136
-        }
-        if (r1 >= 0) {
-            r = r1;                                                    // :91, no ratio test in phase 1
-        } else {
-            q = block_ratio_reduce(q, s);
-            bool elig_nan = false;
-            if (q.elig_row != SPX_NONE) {
-                const double v = __ddiv_rn(b[q.elig_row], col[(int64_t)q.elig_row * stride]);
-                elig_nan = (v != v);
-            }
-            r = ratio_decide(q, elig_nan);                             // :138-141
-        }
-        status = (r < 0) ? SPX_NOCONV : SPX_PIVOT;
-        if (status == SPX_PIVOT) {
-            p = col[(int64_t)r * stride];
-            if (st->npiv >= st->max_pivots) status = SPX_CAP;
-        }
-    }
+    const Decision dec = block_decide(col, stride, b, n, r1, cglob, st->npiv, st->max_pivots, colbuf, s);
     __syncthreads();
     if (threadIdx.x == 0) {
-        st->status = status;
+        st->status = dec.status;
         st->phase1 = (r1 >= 0) ? 1 : 0;
-        if (status == SPX_PIVOT) {
-            st->r = r; st->c = cglob; st->p = p;
+        if (dec.status == SPX_PIVOT) {
+            st->r = dec.r; st->c = cglob; st->p = dec.p;
             const int nslot = (int)((st->npiv + 1) & 1);
             st->slot = nslot;
             st->hint_bneg[nslot] = SPX_NONE;      // the update min-reduces into these
@@ -219,7 +252,7 @@ shard_candidate_kernel(const double *__restrict__ A, const double *__restrict__ 
     }
     if (cloc != SPX_NONE) {
         const double *col = A + cloc;
-        for (int i = threadIdx.x; i <= n; i += PICK_THREADS)
+        for (int i = threadIdx.x; i <= n; i += blockDim.x)
             msg[MSG_HEADER + i] = col[(int64_t)i * ld];
     }
 }
@@ -243,6 +276,148 @@ shard_select_kernel(const double *__restrict__ gathered, int nranks, int64_t msg
     const int64_t cglob = (win < 0) ? -1 : (int64_t)bl;
     const double *col = gathered + (int64_t)(win < 0 ? 0 : win) * msg_doubles + MSG_HEADER;
     block_finish(col, 1, b, n, r1, cglob, st, colbuf, s);
+}
+
+// ---- look-ahead pricing ------------------------------------------------------------
+// Pivot k+1 is chosen from table k WHILE the streaming update of pivot k runs: every cell the
+// choice depends on — the new b column, one new row (f, or the phase-1 row), one new column —
+// is O(n + m) work computed here with exactly the update kernel's arithmetic (same pivot_div,
+// same operation order), so the decision is the one a pick on the finished table k+1 makes.
+// The tableau update then never waits for pricing, and on a column-sharded tableau the
+// all-gather of the candidates is off the critical path as well.
+constexpr int AHEAD_THREADS = 256;   // fits the slot one retiring update CTA frees
+constexpr int AHEAD_BATCH   = 8;     // strided loads in flight per thread while gathering a column
+
+// message layout: [key_hi, key_lo, r1, terminal | new column c' (n+1 cells, f row last)]
+__global__ void __launch_bounds__(AHEAD_THREADS)
+ahead_candidate_kernel(const double *__restrict__ A, const double *__restrict__ bin,
+                       double *__restrict__ bout, int n, int m_loc, int64_t ld, int64_t col0, int rule,
+                       const spx_state *__restrict__ st, const double *__restrict__ colbuf,
+                       double *__restrict__ msg) {
+    __shared__ Scratch s;
+    unsigned long long *h = reinterpret_cast<unsigned long long *>(msg);
+    if (st->status != SPX_PIVOT) {                       // nothing left to price: select copies the state
+        if (threadIdx.x == 0) { h[0] = ~0ull; h[1] = ~0ull; h[2] = ~0ull; h[3] = 1ull; }
+        return;
+    }
+    const int     r  = st->r;
+    const int64_t cl = st->c - col0;                     // local index of the current pivot column
+    const double  p  = st->p;
+    const PivotDiv d = pivot_div_prepare(p);
+    const int nt = (int)blockDim.x;
+
+    // 1. the next '-b' column (replicated on every rank), first negative -> phase-1 row (:72-76)
+    int bneg = SPX_NONE;
+    const double br = bin[r];
+    for (int i = threadIdx.x; i < n; i += nt) {
+        const double bi = bin[i];
+        const double nb = (i == r) ? pivot_div(-bi, d) : cell_update(bi, d, br, colbuf[i]);
+        bout[i] = nb;
+        if (nb < 0.0) bneg = min(bneg, i);
+    }
+    const int rb = block_min_int(bneg, s);
+    const int r1 = (rb == SPX_NONE) ? -1 : rb;
+
+    // 2. the entering column from one row of the NEXT table: the phase-1 row (:82-85) or f (:94-98)
+    const double *rowr = A + (int64_t)r * ld;
+    const int     li   = (r1 >= 0) ? r1 : n;             // which row of the table is priced
+    const double *rowi = A + (int64_t)li * ld;
+    const double  cli  = colbuf[li];
+    auto next_cell = [&](int j) -> double {
+        if (j == cl) return (li == r) ? pivot_cell_update(p) : pivot_div(cli, d);          // :163, :160
+        return (li == r) ? pivot_div(-rowr[j], d) : cell_update(rowi[j], d, rowr[j], cli); // :156, :173-175
+    };
+    int cloc;
+    unsigned long long keyhi = 0ull;
+    if (r1 >= 0) {
+        cloc = block_first_index_fn(m_loc, next_cell, IsPos(), s);
+    } else if (rule == SPX_RULE_REFERENCE) {
+        cloc = block_first_index_fn(m_loc, next_cell, IsNeg(), s);
+    } else {                                             // Dantzig: most negative, lowest index on ties
+        unsigned long long best = ~0ull;
+        for (int j = threadIdx.x; j < m_loc; j += nt) {
+            const double v = next_cell(j);
+            if (v < 0.0) { const unsigned long long k = orderable(v); best = k < best ? k : best; }
+        }
+        best = block_min_u64(best, s);
+        int loc = SPX_NONE;
+        if (best != ~0ull)
+            for (int j = threadIdx.x; j < m_loc; j += nt) {
+                const double v = next_cell(j);
+                if (v < 0.0 && orderable(v) == best) { loc = j; break; }
+            }
+        cloc = block_min_int(loc, s);
+        keyhi = best;
+    }
+    if (threadIdx.x == 0) {
+        h[0] = (cloc == SPX_NONE) ? ~0ull : keyhi;
+        h[1] = (cloc == SPX_NONE) ? ~0ull : (unsigned long long)(col0 + cloc);
+        h[2] = (unsigned long long)(long long)r1;
+        h[3] = 0ull;
+    }
+    if (cloc == SPX_NONE) return;
+
+    // 3. column cloc of the NEXT table (a strided gather of the current one, AHEAD_BATCH loads in flight)
+    const double rj = rowr[cloc];
+    const bool same = (cloc == cl);                      // the column that just left re-enters
+    const double *colp = A + cloc;
+    double *out = msg + MSG_HEADER;
+    for (int base = 0; base <= n; base += nt * AHEAD_BATCH) {
+        double t[AHEAD_BATCH];
+#pragma unroll
+        for (int u = 0; u < AHEAD_BATCH; ++u) {
+            const int i = base + u * nt + (int)threadIdx.x;
+            t[u] = (i <= n && !same) ? colp[(int64_t)i * ld] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < AHEAD_BATCH; ++u) {
+            const int i = base + u * nt + (int)threadIdx.x;
+            if (i <= n) {
+                const double ci = colbuf[i];
+                double v;
+                if (same) v = (i == r) ? pivot_cell_update(p) : pivot_div(ci, d);
+                else      v = (i == r) ? pivot_div(-rj, d) : cell_update(t[u], d, rj, ci);
+                out[i] = v;
+            }
+        }
+    }
+}
+
+// global half: min key over the ranks' messages, ratio test on the winning column with the next b,
+// next state written to st_next (st_cur is still being read by the running update)
+__global__ void __launch_bounds__(AHEAD_THREADS)
+ahead_select_kernel(const double *__restrict__ gathered, int nranks, int64_t msg_doubles,
+                    const double *__restrict__ bnext, int n, const spx_state *__restrict__ st_cur,
+                    spx_state *__restrict__ st_next, double *__restrict__ colbuf_next) {
+    __shared__ Scratch s;
+    const unsigned long long *h0 = reinterpret_cast<const unsigned long long *>(gathered);
+    if (st_cur->status != SPX_PIVOT || h0[3] != 0ull) {
+        if (threadIdx.x == 0) { *st_next = *st_cur; st_next->hint_tag[0] = st_next->hint_tag[1] = -1; }
+        return;
+    }
+    unsigned long long bh = ~0ull, bl = ~0ull; int win = -1;
+    for (int g = 0; g < nranks; ++g) {
+        const unsigned long long *h =
+            reinterpret_cast<const unsigned long long *>(gathered + (int64_t)g * msg_doubles);
+        const unsigned long long kh = h[0], kl = h[1];
+        if (kl != ~0ull && (win < 0 || kh < bh || (kh == bh && kl < bl))) { bh = kh; bl = kl; win = g; }
+    }
+    const int r1 = (int)(long long)h0[2];
+    const int64_t cglob = (win < 0) ? -1 : (int64_t)bl;
+    const double *col = gathered + (int64_t)(win < 0 ? 0 : win) * msg_doubles + MSG_HEADER;
+    const int64_t npiv = st_cur->npiv + 1;               // pivots applied to the table being priced
+    const int64_t cap  = st_cur->max_pivots;
+    const Decision dec = block_decide(col, 1, bnext, n, r1, cglob, npiv, cap, colbuf_next, s);
+    if (threadIdx.x == 0) {
+        spx_state o;
+        o.status = dec.status; o.r = dec.r; o.c = cglob; o.p = dec.p;
+        o.npiv = npiv; o.max_pivots = cap; o.phase1 = (r1 >= 0) ? 1 : 0; o.slot = 0;
+        o.hint_tag[0] = o.hint_tag[1] = -1;
+        o.hint_bneg[0] = o.hint_bneg[1] = SPX_NONE;
+        o.hint_fneg[0] = o.hint_fneg[1] = SPX_NONE;
+        for (int q = 0; q < 6; ++q) o.reserved[q] = 0;
+        *st_next = o;
+    }
 }
 
 } // namespace
@@ -275,6 +450,24 @@ cudaError_t shard_select(const double *gathered, int nranks, const double *b, in
                          spx_state *st, double *colbuf, cudaStream_t stream) {
     shard_select_kernel<<<1, PICK_THREADS, 0, stream>>>(gathered, nranks, shard_msg_doubles(n), b,
                                                         n, sticky, st, colbuf);
+    spx_host::count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t ahead_candidate(const double *A, const double *bin, double *bout, int n, int m_loc,
+                            int64_t ld, int64_t col0, int rule, const spx_state *st,
+                            const double *colbuf, double *msg, cudaStream_t stream) {
+    ahead_candidate_kernel<<<1, AHEAD_THREADS, 0, stream>>>(A, bin, bout, n, m_loc, ld, col0, rule, st,
+                                                            colbuf, msg);
+    spx_host::count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t ahead_select(const double *gathered, int nranks, const double *bnext, int n,
+                         const spx_state *st_cur, spx_state *st_next, double *colbuf_next,
+                         cudaStream_t stream) {
+    ahead_select_kernel<<<1, AHEAD_THREADS, 0, stream>>>(gathered, nranks, shard_msg_doubles(n), bnext, n,
+                                                         st_cur, st_next, colbuf_next);
     spx_host::count_launch();
     return cudaGetLastError();
 }

@@ -78,20 +78,24 @@ __device__ __forceinline__ void update_b_rows(const double *__restrict__ bin, do
 }
 
 // commit: labels (:152), trace, pivot counter — one thread of one CTA
+// ahead != 0: the look-ahead kernels own the state and the b column (the next state is written
+// by ahead_select_kernel while this kernel still reads the current one), so nothing is stored to *st
 __device__ __forceinline__ void commit_pivot(spx_state *st, int r, int64_t cg, int slot,
-                                             int32_t *rowlab, int32_t *collab, int32_t *trace) {
+                                             int32_t *rowlab, int32_t *collab, int32_t *trace, int ahead) {
     const int64_t k = st->npiv;
     const int32_t tmp = rowlab[cg]; rowlab[cg] = collab[r]; collab[r] = tmp;
     if (trace) { trace[2 * k] = r; trace[2 * k + 1] = (int32_t)cg; }
-    st->hint_tag[slot] = k + 1;
-    st->npiv = k + 1;
+    if (!ahead) {
+        st->hint_tag[slot] = k + 1;
+        st->npiv = k + 1;
+    }
 }
 
 template <int MINB>
 __global__ void __launch_bounds__(UPD_THREADS, MINB)
 update_tiled_kernel(const double *__restrict__ Ain, double *__restrict__ Aout,
                     const double *__restrict__ bin, double *__restrict__ bout,
-                    int n, int m_loc, int64_t ld, int64_t col0, int tr,
+                    int n, int m_loc, int64_t ld, int64_t col0, int tr, int ahead,
                     spx_state *st, const double *__restrict__ colbuf,
                     int32_t *__restrict__ rowlab, int32_t *__restrict__ collab,
                     int32_t *__restrict__ trace) {
@@ -174,16 +178,16 @@ update_tiled_kernel(const double *__restrict__ Ain, double *__restrict__ Aout,
             }
         }
     }
-    if (has_f) {                                         // this tile holds the f row (CTA-uniform)
+    if (has_f && !ahead) {                               // this tile holds the f row (CTA-uniform)
         const int w = __reduce_min_sync(0xffffffffu, fneg);
         if ((tid & 31) == 0 && w != SPX_NONE) atomicMin(&st->hint_fneg[slot], w);
     }
 
     // ---- the '-b' column: column tile 0 does it
     if (blockIdx.x == 0) {
-        if (tid < 64)                                    // warps 0,1 cover tr <= 64 rows
+        if (tid < 64 && !ahead)                          // warps 0,1 cover tr <= 64 rows
             update_b_rows(bin, bout, colbuf, n, r, d, i0 + tid, tid < rows, &st->hint_bneg[slot]);
-        if (blockIdx.y == 0 && tid == 0) commit_pivot(st, r, cg, slot, rowlab, collab, trace);
+        if (blockIdx.y == 0 && tid == 0) commit_pivot(st, r, cg, slot, rowlab, collab, trace, ahead);
     }
 }
 
@@ -230,7 +234,7 @@ __device__ __forceinline__ TileIter make_iter(int n_ct, int n_rt, int order) {
 __global__ void __launch_bounds__(PIPE_THREADS, 1)
 update_pipelined_kernel(const double *__restrict__ Ain, double *__restrict__ Aout,
                         const double *__restrict__ bin, double *__restrict__ bout,
-                        int n, int m_loc, int64_t ld, int64_t col0, int order,
+                        int n, int m_loc, int64_t ld, int64_t col0, int order, int ahead,
                         spx_state *st, const double *__restrict__ colbuf,
                         int32_t *__restrict__ rowlab, int32_t *__restrict__ collab,
                         int32_t *__restrict__ trace) {
@@ -342,12 +346,13 @@ update_pipelined_kernel(const double *__restrict__ Ain, double *__restrict__ Aou
             }
         }
     }
-    if (saw_f && fneg != SPX_NONE) atomicMin(&st->hint_fneg[slot], fneg);
+    if (saw_f && fneg != SPX_NONE && !ahead) atomicMin(&st->hint_fneg[slot], fneg);
 
     // ---- the '-b' column, spread over the consumer threads of all CTAs
-    for (int base = blockIdx.x * PIPE_CONSUMERS; base < n; base += gridDim.x * PIPE_CONSUMERS)
-        update_b_rows(bin, bout, colbuf, n, r, d, base + tid, true, &st->hint_bneg[slot]);
-    if (blockIdx.x == 0 && tid == 0) commit_pivot(st, r, cg, slot, rowlab, collab, trace);
+    if (!ahead)
+        for (int base = blockIdx.x * PIPE_CONSUMERS; base < n; base += gridDim.x * PIPE_CONSUMERS)
+            update_b_rows(bin, bout, colbuf, n, r, d, base + tid, true, &st->hint_bneg[slot]);
+    if (blockIdx.x == 0 && tid == 0) commit_pivot(st, r, cg, slot, rowlab, collab, trace, ahead);
 }
 
 // a / p for arrays: the self-test of pivot_div against the compiler's div.rn.f64
@@ -454,7 +459,7 @@ int set_option(int key, int64_t value) {
 
 cudaError_t update(const double *Ain, double *Aout, const double *bin, double *bout, int n,
                    int m_loc, int64_t ld, int64_t col0, spx_state *st, const double *colbuf,
-                   int32_t *rowlab, int32_t *collab, int32_t *trace, cudaStream_t stream) {
+                   int32_t *rowlab, int32_t *collab, int32_t *trace, int ahead, cudaStream_t stream) {
     int kernel = (int)g_opt[SPX_OPT_UPDATE_KERNEL];
     // measured on B200 (profiles/): the tiled kernel streams at the copy rate already; the
     // pipelined kernel stays selectable for experiments
@@ -472,7 +477,7 @@ cudaError_t update(const double *Ain, double *Aout, const double *bin, double *b
         if (tiles < grid) grid = tiles;
         if (grid < 1) grid = 1;                       // a shard with no columns still updates b
         update_pipelined_kernel<<<(unsigned)grid, PIPE_THREADS, PIPE_SMEM, stream>>>(
-            Ain, Aout, bin, bout, n, m_loc, ld, col0, (int)g_opt[SPX_OPT_PIPE_ORDER], st, colbuf,
+            Ain, Aout, bin, bout, n, m_loc, ld, col0, (int)g_opt[SPX_OPT_PIPE_ORDER], ahead, st, colbuf,
             rowlab, collab, trace);
         spx_host::count_launch();
         return cudaGetLastError();
@@ -482,7 +487,7 @@ cudaError_t update(const double *Ain, double *Aout, const double *bin, double *b
     if (grid.x == 0) grid.x = 1;      // a shard with no columns still updates b
 #define SPX_LAUNCH_TILED(MINB)                                                                      \
     update_tiled_kernel<MINB><<<grid, UPD_THREADS, 0, stream>>>(Ain, Aout, bin, bout, n, m_loc, ld, \
-                                                               col0, tr, st, colbuf, rowlab, collab, trace)
+                                                               col0, tr, ahead, st, colbuf, rowlab, collab, trace)
     switch ((int)g_opt[SPX_OPT_TILED_MIN_BLOCKS]) {
     case 1: SPX_LAUNCH_TILED(1); break;
     case 2: SPX_LAUNCH_TILED(2); break;

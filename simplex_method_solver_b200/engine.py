@@ -73,9 +73,18 @@ class DeviceTableau:
             self.obj = torch.empty(2, dtype=torch.float64, device=dev)
             self.trace = (torch.empty((trace_capacity, 2), dtype=torch.int32, device=dev)
                           if trace_capacity > 0 else None)
+            self.work = torch.zeros(int(L.spx_solve_workspace_bytes(self.n)) // 8, dtype=torch.float64,
+                                    device=dev)
         self.trace_capacity = int(trace_capacity)
         self.max_pivots = int(max_pivots)
         self._keepalive = None
+
+    # look-ahead pays when one update is long enough to hide the side-stream pricing and the
+    # extra enqueues per pivot; small (L2-resident) tableaus keep the classic two-launch loop
+    LOOKAHEAD_MIN_BYTES = 256 << 20
+
+    def lookahead_default(self) -> bool:
+        return (self.n + 1) * self.ld * 8 >= self.LOOKAHEAD_MIN_BYTES
 
     # -- plumbing ---------------------------------------------------------------
     def _stream(self) -> int:
@@ -131,17 +140,24 @@ class DeviceTableau:
         self._call("spx_update", self.A[c].data_ptr(), self.A[c ^ 1].data_ptr(),
                    self.b[c].data_ptr(), self.b[c ^ 1].data_ptr(), self.n, self.m, self.ld,
                    self.state.data_ptr(), self.colbuf.data_ptr(), self.rowlab.data_ptr(),
-                   self.collab.data_ptr(), N.ptr(self.trace))
+                   self.collab.data_ptr(), N.ptr(self.trace) if npiv < self.trace_capacity else None)
 
     # -- the loop -------------------------------------------------------------------
-    def solve(self, rule: int = N.RULE_REFERENCE, chunk: int = 64, stop_after: int = 0):
-        """Run pick+update pairs on the device until a terminal status / cap / stop_after."""
+    def solve(self, rule: int = N.RULE_REFERENCE, chunk: int = 64, stop_after: int = 0,
+              lookahead=None):
+        """Run the pivot loop on the device until a terminal status / cap / stop_after.
+
+        lookahead: price pivot k+1 on a side stream while update k streams (None: by size).
+        """
         st, npiv = ctypes.c_int32(0), ctypes.c_int64(0)
+        if lookahead is None:
+            lookahead = self.lookahead_default()
+        work, wbytes = (self.work.data_ptr(), self.work.numel() * 8) if lookahead else (None, 0)
         with torch.cuda.device(self.device):
             N.call("spx_solve", self.A[0].data_ptr(), self.A[1].data_ptr(), self.b[0].data_ptr(),
                    self.b[1].data_ptr(), self.n, self.m, self.ld, rule, self.state.data_ptr(),
                    self.colbuf.data_ptr(), self.rowlab.data_ptr(), self.collab.data_ptr(),
-                   N.ptr(self.trace), int(chunk), int(stop_after), ctypes.byref(st),
+                   N.ptr(self.trace), int(chunk), int(stop_after), work, wbytes, ctypes.byref(st),
                    ctypes.byref(npiv), self._stream())
         return st.value, npiv.value
 

@@ -86,7 +86,7 @@ class CudaShardOps:
     def update(self, Ain, Aout, bin_, bout, n, m_loc, ld, col0, state, colbuf, rowlab, collab, trace):
         N.call("spx_shard_update", Ain.data_ptr(), Aout.data_ptr(), bin_.data_ptr(), bout.data_ptr(),
                n, m_loc, ld, col0, state.data_ptr(), colbuf.data_ptr(), rowlab.data_ptr(),
-               collab.data_ptr(), N.ptr(trace), self._stream())
+               collab.data_ptr(), N.ptr(trace), 0, self._stream())
 
 
 class ShardedTableau:

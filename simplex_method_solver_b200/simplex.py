@@ -120,7 +120,15 @@ class SimplexMethod:
     # ------------------------------------------------------------------ K1+K2
     def _pick_state(self):
         self._dev.pick(self._npiv, self._rule, sticky=False)
-        return self._dev.read_state()
+        st = self._dev.read_state()
+        if st.status == N.CAP:
+            # the cap belongs to solve()/get_solution(); the reference's step API has none
+            st.max_pivots = 1 << 62
+            st.status = N.PIVOT
+            self._dev.write_state(st)
+            self._dev.pick(self._npiv, self._rule, sticky=False)
+            st = self._dev.read_state()
+        return st
 
     def pick_element(self):                                  # :70-141
         st = self._pick_state()
@@ -252,7 +260,7 @@ class SimplexMethod:
                 flat[self.m: self.n * (self.m + 1): self.m + 1] = b
             self._append_info(result, int(st.r), int(st.c), flat, snapshots)
 
-    def solve(self, max_pivots=None, chunk: int = 64, trace: bool = True) -> Solution:
+    def solve(self, max_pivots=None, chunk: int = 64, trace: bool = True, lookahead=None) -> Solution:
         """Device-side loop without snapshots: status, pivot trace, x[0..m), objective.
 
         Continues from the current table; the pivot loop runs as pre-enqueued
@@ -267,7 +275,8 @@ class SimplexMethod:
                 old = dev.trace
                 dev.trace = torch.zeros((need, 2), dtype=torch.int32, device=dev.device)
                 if old is not None and start > 0:
-                    dev.trace[:start].copy_(old[:start])
+                    keep = min(start, old.shape[0])     # step-API pivots beyond the old capacity are not traced
+                    dev.trace[:keep].copy_(old[:keep])
                 dev.trace_capacity = need
         else:
             dev.trace = None
@@ -277,7 +286,7 @@ class SimplexMethod:
         if st.status == N.CAP:
             st.status = N.PIVOT
         dev.write_state(st)
-        status, npiv = dev.solve(self._rule, chunk=chunk)
+        status, npiv = dev.solve(self._rule, chunk=chunk, lookahead=lookahead)
         self._npiv = int(npiv)
         self._table_cache = None
         sol = dev.solution(status, self._npiv)

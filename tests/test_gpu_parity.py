@@ -72,13 +72,15 @@ def test_cfg1_snapshot_digest(spx, ref_cases):
 
 
 # --------------------------------------------------------------------------- all golden cases
-def test_all_reference_cases_streaming_solver(spx, ref_cases):
-    """solve(): device-side pick+update loop; trace, ending, labels, final table bits."""
+@pytest.mark.parametrize("lookahead,chunk", [(False, 7), (True, 7), (True, 4), (True, 1)])
+def test_all_reference_cases_streaming_solver(spx, ref_cases, lookahead, chunk):
+    """solve(): device-side loop, classic (pick k, update k, ...) and look-ahead (pivot k+1 priced
+    from table k on a side stream while update k runs); trace, ending, labels, final table bits."""
     for case in ref_cases:
         rows, c = case_inputs(case)
         n, m = rows.shape[0], rows.shape[1] - 1
         sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
-        sol = sm.solve(max_pivots=case["cap"], chunk=7)
+        sol = sm.solve(max_pivots=case["cap"], chunk=chunk, lookahead=lookahead)
         assert sol.status == END_TO_STATUS[case["end"]], case["name"]
         assert sol.trace.tolist() == case["trace"], case["name"]
         flat = sm._dev.export_flat(sm._npiv)
@@ -144,6 +146,37 @@ def test_step_api_matches_oracle(spx):
                 with pytest.raises(ValueError, match=oracle.STATUS_NAME[st]):
                     sm.recalculate_matrix()
                 break
+
+
+def test_lookahead_state_feeds_the_step_api_and_resumes(spx):
+    """A look-ahead solve stopped by the cap leaves a state the step API and a resumed solve continue from."""
+    rows, c = W.dense_lp(40, 70, 9)
+    ref = oracle.solve(rows, c, max_pivots=10000)
+    assert ref.status == oracle.OPTIMAL and ref.npiv > 25
+    sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
+    sol = sm.solve(max_pivots=11, chunk=4, lookahead=True)
+    assert sol.status == spx.N.CAP and sol.trace.tolist() == ref.trace[:11].tolist()
+    ok, r, cc, e = sm.pick_element()
+    assert ok and [r, cc] == ref.trace[11].tolist()
+    sm.recalculate_matrix()
+    sol = sm.solve(max_pivots=10000, chunk=5, lookahead=True)
+    assert sol.status == spx.N.OPTIMAL and sol.npiv == ref.npiv
+    # pivot 11 went through the step API after the traced capacity of the first solve: not traced
+    assert sol.trace[:11].tolist() == ref.trace[:11].tolist()
+    assert sol.trace[12:].tolist() == ref.trace[12:].tolist()
+    assert np.array_equal(bits(sm._dev.export_flat(sm._npiv)), bits(ref.table))
+    assert sol.x.tobytes() == ref.x.tobytes()
+
+
+@pytest.mark.parametrize("lookahead", [False, True])
+def test_dantzig_rule_modes_agree(spx, lookahead):
+    """rule='dantzig' (extension, not reference behaviour): classic and look-ahead give one trace."""
+    rows, c = W.dense_lp(30, 50, 4)
+    a = spx.simplex.SimplexMethod(rows, c, engine="stream", rule="dantzig").solve(max_pivots=500, chunk=9,
+                                                                                  lookahead=lookahead)
+    b = spx.batched.solve_batched(flat_of(rows, c)[None, :], 30, 50, max_pivots=500, rule="dantzig")
+    assert a.status == b.status[0] == 0 and a.npiv == b.npiv[0]
+    assert a.trace.tolist() == b.trace[0, : a.npiv].tolist()
 
 
 def test_inputs_not_mutated_and_attributes(spx):
@@ -306,17 +339,18 @@ def test_every_update_kernel_variant_is_bit_exact(spx, opts):
 
 
 # --------------------------------------------------------------------------- BASELINE configs
-def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests):
+@pytest.mark.parametrize("lookahead", [False, True])
+def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests, lookahead):
     g = cfg_digests["cfg2"]
     rows, c = W.dense_lp(1000, 2000, 0)
     assert W.input_digest(rows, c) == g["input_sha256"]
     sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
     # the reference's own first 12 pivots and its table after them
-    sol = sm.solve(max_pivots=12, chunk=12)
+    sol = sm.solve(max_pivots=12, chunk=12, lookahead=lookahead)
     assert sol.trace.tolist() == g["reference_first12"]["trace"]
     assert table_sha(sm._dev.export_flat(sm._npiv)) == g["reference_first12"]["table_sha256_after12"]
     # continue to optimality
-    sol = sm.solve(max_pivots=200000 - 12, chunk=256)
+    sol = sm.solve(max_pivots=200000 - 12, chunk=255, lookahead=lookahead)
     o = g["oracle_full"]
     assert sol.status == o["status"] == 0 and sol.npiv == o["npiv"] == 13579
     assert W.pivot_digest(sol.trace[:100]) == o["pivot_sha256_after100"]
@@ -363,10 +397,11 @@ def test_cfg5_klee_minty(spx, cfg_digests, n):
     assert res.x[0, n - 1] == float(5 ** n) and (res.x[0, : n - 1] == 0).all()
 
 
-def test_cfg5_klee_minty10_streaming_equals_batched(spx, cfg_digests):
+@pytest.mark.parametrize("lookahead", [False, True])
+def test_cfg5_klee_minty10_streaming_equals_batched(spx, cfg_digests, lookahead):
     rows, c = W.klee_minty(10)
     sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
-    sol = sm.solve(max_pivots=2000, chunk=128)
+    sol = sm.solve(max_pivots=2000, chunk=127, lookahead=lookahead)
     assert sol.status == 0 and sol.npiv == 1023
     assert W.pivot_digest(sol.trace) == cfg_digests["km10"]["pivot_sha256"]
     assert table_sha(sm._dev.export_flat(sm._npiv)) == cfg_digests["km10"]["final_table_sha256"]
@@ -378,8 +413,8 @@ def test_cfg4_16k_x_32k_prefix(spx, cfg_digests):
     n, m = 16384, 32768
     rows, c = W.dense_lp(n, m, 0)
     assert W.input_digest(rows, c) == g["input_sha256"]
-    dev = spx.engine.DeviceTableau(n, m, trace_capacity=200)
-    dev.load(rows, c, max_pivots=200)
+    dev = spx.engine.DeviceTableau(n, m, trace_capacity=256)
+    dev.load(rows, c, max_pivots=256)       # look-ahead prices pivot 201: keep the cap out of the way
     del rows
     dev.pick(0)
     s = dev.read_state()
