@@ -336,7 +336,8 @@ def run_ours(args):
 
     # ---------------- N > 1: column-sharded, one process per GPU ---------------------------
     from simplex_method_solver_b200.parallel import ShardedTableau
-    sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
+    sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
+                        lookahead=not args.no_lookahead)
     sh.load(rows, c, max_pivots=need + 64)
     del rows
     for _ in range(args.warmup):
@@ -358,7 +359,7 @@ def run_ours(args):
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    st = sh.read_state()
+    st = sh.sync()
     assert st.npiv == need and st.status == N.PIVOT, (st.status, st.npiv)
     tr = sh.trace[:need].cpu().numpy()
     k = min(need, len(gold))
@@ -392,6 +393,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-pivots-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lookahead", action="store_true",
+                    help="classic pick->update order instead of pricing pivot k+1 during update k")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: the timing rules ask for >= 3 warm-up steps")

@@ -19,6 +19,7 @@ using namespace spx;
 constexpr int PICK_THREADS = 1024;
 constexpr int PICK_WARPS   = PICK_THREADS / 32;
 constexpr int MSG_HEADER   = 4;      // doubles: [key_hi, key_lo, r_phase1, reserved]
+constexpr int GATHER_BATCH = 8;      // independent loads in flight per thread in the O(n) loops
 
 struct Scratch {
     int                red_i[PICK_WARPS];
@@ -177,10 +178,24 @@ __device__ Decision block_decide(const double *__restrict__ col, int64_t stride,
         return dec;
     }
     Ratio q = ratio_identity();
-    for (int i = threadIdx.x; i <= n; i += blockDim.x) {
-        const double a = col[(int64_t)i * stride];
-        colbuf[i] = a;
-        if (r1 < 0 && i < n) ratio_accumulate(q, i, a, b[i]);          // :111-136
+    // GATHER_BATCH independent (strided) loads in flight per thread: the loop is latency-bound
+    const int nt = (int)blockDim.x;
+    for (int base = 0; base <= n; base += nt * GATHER_BATCH) {
+        double a[GATHER_BATCH], bb[GATHER_BATCH];
+#pragma unroll
+        for (int u = 0; u < GATHER_BATCH; ++u) {
+            const int i = base + u * nt + (int)threadIdx.x;
+            a[u]  = (i <= n) ? col[(int64_t)i * stride] : 0.0;
+            bb[u] = (r1 < 0 && i < n) ? b[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < GATHER_BATCH; ++u) {
+            const int i = base + u * nt + (int)threadIdx.x;
+            if (i <= n) {
+                colbuf[i] = a[u];
+                if (r1 < 0 && i < n) ratio_accumulate(q, i, a[u], bb[u]);   // :111-136
+            }
+        }
     }
     int r;
     if (r1 >= 0) {
@@ -252,8 +267,20 @@ shard_candidate_kernel(const double *__restrict__ A, const double *__restrict__ 
     }
     if (cloc != SPX_NONE) {
         const double *col = A + cloc;
-        for (int i = threadIdx.x; i <= n; i += blockDim.x)
-            msg[MSG_HEADER + i] = col[(int64_t)i * ld];
+        const int nt = (int)blockDim.x;
+        for (int base = 0; base <= n; base += nt * GATHER_BATCH) {
+            double t[GATHER_BATCH];
+#pragma unroll
+            for (int u = 0; u < GATHER_BATCH; ++u) {
+                const int i = base + u * nt + (int)threadIdx.x;
+                t[u] = (i <= n) ? col[(int64_t)i * ld] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < GATHER_BATCH; ++u) {
+                const int i = base + u * nt + (int)threadIdx.x;
+                if (i <= n) msg[MSG_HEADER + i] = t[u];
+            }
+        }
     }
 }
 
@@ -286,10 +313,9 @@ shard_select_kernel(const double *__restrict__ gathered, int nranks, int64_t msg
 // The tableau update then never waits for pricing, and on a column-sharded tableau the
 // all-gather of the candidates is off the critical path as well.
 constexpr int AHEAD_THREADS = 256;   // fits the slot one retiring update CTA frees
-constexpr int AHEAD_BATCH   = 8;     // strided loads in flight per thread while gathering a column
 
 // message layout: [key_hi, key_lo, r1, terminal | new column c' (n+1 cells, f row last)]
-__global__ void __launch_bounds__(AHEAD_THREADS)
+__global__ void __launch_bounds__(AHEAD_THREADS, 3)
 ahead_candidate_kernel(const double *__restrict__ A, const double *__restrict__ bin,
                        double *__restrict__ bout, int n, int m_loc, int64_t ld, int64_t col0, int rule,
                        const spx_state *__restrict__ st, const double *__restrict__ colbuf,
@@ -309,11 +335,23 @@ ahead_candidate_kernel(const double *__restrict__ A, const double *__restrict__ 
     // 1. the next '-b' column (replicated on every rank), first negative -> phase-1 row (:72-76)
     int bneg = SPX_NONE;
     const double br = bin[r];
-    for (int i = threadIdx.x; i < n; i += nt) {
-        const double bi = bin[i];
-        const double nb = (i == r) ? pivot_div(-bi, d) : cell_update(bi, d, br, colbuf[i]);
-        bout[i] = nb;
-        if (nb < 0.0) bneg = min(bneg, i);
+    for (int base = 0; base < n; base += nt * GATHER_BATCH) {
+        double bi[GATHER_BATCH], ci[GATHER_BATCH];
+#pragma unroll
+        for (int u = 0; u < GATHER_BATCH; ++u) {
+            const int i = base + u * nt + (int)threadIdx.x;
+            bi[u] = (i < n) ? bin[i] : 0.0;
+            ci[u] = (i < n) ? colbuf[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < GATHER_BATCH; ++u) {
+            const int i = base + u * nt + (int)threadIdx.x;
+            if (i < n) {
+                const double nb = (i == r) ? pivot_div(-bi[u], d) : cell_update(bi[u], d, br, ci[u]);
+                bout[i] = nb;
+                if (nb < 0.0) bneg = min(bneg, i);
+            }
+        }
     }
     const int rb = block_min_int(bneg, s);
     const int r1 = (rb == SPX_NONE) ? -1 : rb;
@@ -357,23 +395,24 @@ ahead_candidate_kernel(const double *__restrict__ A, const double *__restrict__ 
     }
     if (cloc == SPX_NONE) return;
 
-    // 3. column cloc of the NEXT table (a strided gather of the current one, AHEAD_BATCH loads in flight)
+    // 3. column cloc of the NEXT table (a strided gather of the current one, GATHER_BATCH loads in flight)
     const double rj = rowr[cloc];
     const bool same = (cloc == cl);                      // the column that just left re-enters
     const double *colp = A + cloc;
     double *out = msg + MSG_HEADER;
-    for (int base = 0; base <= n; base += nt * AHEAD_BATCH) {
-        double t[AHEAD_BATCH];
+    for (int base = 0; base <= n; base += nt * GATHER_BATCH) {
+        double t[GATHER_BATCH], cc[GATHER_BATCH];
 #pragma unroll
-        for (int u = 0; u < AHEAD_BATCH; ++u) {
+        for (int u = 0; u < GATHER_BATCH; ++u) {
             const int i = base + u * nt + (int)threadIdx.x;
-            t[u] = (i <= n && !same) ? colp[(int64_t)i * ld] : 0.0;
+            t[u]  = (i <= n && !same) ? colp[(int64_t)i * ld] : 0.0;
+            cc[u] = (i <= n) ? colbuf[i] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < AHEAD_BATCH; ++u) {
+        for (int u = 0; u < GATHER_BATCH; ++u) {
             const int i = base + u * nt + (int)threadIdx.x;
             if (i <= n) {
-                const double ci = colbuf[i];
+                const double ci = cc[u];
                 double v;
                 if (same) v = (i == r) ? pivot_cell_update(p) : pivot_div(ci, d);
                 else      v = (i == r) ? pivot_div(-rj, d) : cell_update(t[u], d, rj, ci);
@@ -385,7 +424,7 @@ ahead_candidate_kernel(const double *__restrict__ A, const double *__restrict__ 
 
 // global half: min key over the ranks' messages, ratio test on the winning column with the next b,
 // next state written to st_next (st_cur is still being read by the running update)
-__global__ void __launch_bounds__(AHEAD_THREADS)
+__global__ void __launch_bounds__(AHEAD_THREADS, 3)
 ahead_select_kernel(const double *__restrict__ gathered, int nranks, int64_t msg_doubles,
                     const double *__restrict__ bnext, int n, const spx_state *__restrict__ st_cur,
                     spx_state *__restrict__ st_next, double *__restrict__ colbuf_next) {

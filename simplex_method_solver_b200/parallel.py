@@ -17,12 +17,20 @@ Two partitionings, the two places where the pivot loop shards naturally
   data-dependent broadcast root.  The pivot trace equals the single-GPU trace
   exactly (tests/test_sharded_gloo.py on CPU with gloo; bench.py on GPUs).
 
+  With ``lookahead=True`` the exchange leaves the critical path: pivot k+1 is
+  priced from table k (the look-ahead kernels of csrc/spx_pick.cu compute the
+  next b column, the next f / phase-1 row and the next entering column with the
+  update's own arithmetic), so candidate -> all-gather -> select run on a
+  high-priority side stream WHILE update k streams on the main stream; state and
+  colbuf are double-buffered and the two streams join once per pivot.
+
 The kernels are reached through ``ShardOps``; the product implementation
 (``CudaShardOps``) calls the C ABI.  Tests inject a CPU stand-in to exercise
 this file's collective logic under gloo without a GPU.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from typing import Optional
 
@@ -83,21 +91,31 @@ class CudaShardOps:
         N.call("spx_shard_select", gathered.data_ptr(), world, b.data_ptr(), n, rule, 1,
                state.data_ptr(), colbuf.data_ptr(), self._stream())
 
-    def update(self, Ain, Aout, bin_, bout, n, m_loc, ld, col0, state, colbuf, rowlab, collab, trace):
+    def update(self, Ain, Aout, bin_, bout, n, m_loc, ld, col0, state, colbuf, rowlab, collab, trace,
+               ahead=False):
         N.call("spx_shard_update", Ain.data_ptr(), Aout.data_ptr(), bin_.data_ptr(), bout.data_ptr(),
                n, m_loc, ld, col0, state.data_ptr(), colbuf.data_ptr(), rowlab.data_ptr(),
-               collab.data_ptr(), N.ptr(trace), 0, self._stream())
+               collab.data_ptr(), N.ptr(trace), int(ahead), self._stream())
+
+    def ahead_candidate(self, A, bin_, bout, n, m_loc, ld, col0, rule, state, colbuf, send):
+        N.call("spx_ahead_candidate", A.data_ptr(), bin_.data_ptr(), bout.data_ptr(), n, m_loc, ld, col0,
+               rule, state.data_ptr(), colbuf.data_ptr(), send.data_ptr(), self._stream())
+
+    def ahead_select(self, gathered, world, bnext, n, state_cur, state_next, colbuf_next):
+        N.call("spx_ahead_select", gathered.data_ptr(), world, bnext.data_ptr(), n, state_cur.data_ptr(),
+               state_next.data_ptr(), colbuf_next.data_ptr(), self._stream())
 
 
 class ShardedTableau:
     """One rank's share of a column-sharded tableau plus the replicated pieces."""
 
     def __init__(self, n: int, m: int, rank: int, world: int, device, trace_capacity: int = 0,
-                 group=None, ops=None, rule: int = N.RULE_REFERENCE):
+                 group=None, ops=None, rule: int = N.RULE_REFERENCE, lookahead: bool = False):
         self.n, self.m, self.rank, self.world = int(n), int(m), int(rank), int(world)
         self.device = torch.device(device)
         self.group = group
         self.rule = rule
+        self.lookahead = bool(lookahead)
         self.ops = ops if ops is not None else CudaShardOps(self.device)
         self.col0, self.m_loc = column_block(self.m, self.rank, self.world)
         self.ld = max(16, (self.m_loc + 15) // 16 * 16)
@@ -115,6 +133,15 @@ class ShardedTableau:
         self.gathered = torch.zeros((self.world, self.msgd), dtype=f64, device=dev)
         self.trace = torch.zeros((trace_capacity, 2), dtype=i32, device=dev) if trace_capacity > 0 else None
         self.npiv_enqueued = 0
+        # look-ahead: second state / colbuf, the side stream and the fork/join events
+        self.states = [self.state, torch.zeros_like(self.state)]
+        self.colbufs = [self.colbuf, torch.zeros_like(self.colbuf)]
+        self.si = 0                  # which of the two holds the decision for the current table
+        self.priced = False
+        self.side = self.fork = self.join = None
+        if self.lookahead and self.device.type == "cuda":
+            self.side = torch.cuda.Stream(device=self.device, priority=-1)
+            self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
 
     def load(self, rows: np.ndarray, function: np.ndarray, max_pivots: int):
         """Every rank reads its own column block (and the whole b column) of the same host table."""
@@ -123,20 +150,79 @@ class ShardedTableau:
                               self.n, self.m, self.col0, self.m_loc, self.ld)
         self.ops.init_state(self.state, self.rowlab, self.collab, self.n, self.m, int(max_pivots))
         self.npiv_enqueued = 0
+        self.si, self.priced = 0, False
 
-    def step(self):
-        """One pivot: candidate -> all-gather -> select -> update.  Asynchronous on a GPU."""
-        cur = self.npiv_enqueued & 1
-        self.ops.candidate(self.A[cur], self.b[cur], self.n, self.m_loc, self.ld, self.col0, self.rule,
-                           self.state, self.send)
+    def _all_gather(self):
         if self.world > 1:
             dist.all_gather_into_tensor(self.gathered.view(-1), self.send, group=self.group)
         else:
             self.gathered[0].copy_(self.send)
-        self.ops.select(self.gathered, self.world, self.b[cur], self.n, self.rule, self.state, self.colbuf)
-        self.ops.update(self.A[cur], self.A[cur ^ 1], self.b[cur], self.b[cur ^ 1], self.n, self.m_loc,
-                        self.ld, self.col0, self.state, self.colbuf, self.rowlab, self.collab, self.trace)
+
+    def _on_side(self):
+        """Context that makes the side stream current (no-op for the CPU stand-in)."""
+        return torch.cuda.stream(self.side) if self.side is not None else contextlib.nullcontext()
+
+    # A pivot is three phases so that tests can emulate several ranks in one process by running
+    # each phase for every rank in lockstep: local half -> exchange -> global half + update.
+    def phase_local(self):
+        cur = self.npiv_enqueued & 1
+        if not self.lookahead:
+            self.ops.candidate(self.A[cur], self.b[cur], self.n, self.m_loc, self.ld, self.col0, self.rule,
+                               self.state, self.send)
+            return
+        S, C, si = self.states, self.colbufs, self.si
+        if self.side is not None:
+            self.fork.record(torch.cuda.current_stream(self.device))
+            self.side.wait_event(self.fork)
+        with self._on_side():
+            self.ops.ahead_candidate(self.A[cur], self.b[cur], self.b[cur ^ 1], self.n, self.m_loc, self.ld,
+                                     self.col0, self.rule, S[si], C[si], self.send)
+
+    def phase_exchange(self, gather=None):
+        with (self._on_side() if self.lookahead else contextlib.nullcontext()):
+            (gather or self._all_gather)()
+
+    def phase_global(self):
+        cur = self.npiv_enqueued & 1
+        if not self.lookahead:
+            self.ops.select(self.gathered, self.world, self.b[cur], self.n, self.rule, self.state, self.colbuf)
+            self.ops.update(self.A[cur], self.A[cur ^ 1], self.b[cur], self.b[cur ^ 1], self.n, self.m_loc,
+                            self.ld, self.col0, self.state, self.colbuf, self.rowlab, self.collab, self.trace)
+        else:
+            S, C, si = self.states, self.colbufs, self.si
+            with self._on_side():
+                self.ops.ahead_select(self.gathered, self.world, self.b[cur ^ 1], self.n, S[si], S[si ^ 1],
+                                      C[si ^ 1])
+                if self.side is not None:
+                    self.join.record(self.side)
+            # the streaming update of pivot k: main stream, concurrent with the pricing above
+            self.ops.update(self.A[cur], self.A[cur ^ 1], self.b[cur], self.b[cur ^ 1], self.n, self.m_loc,
+                            self.ld, self.col0, S[si], C[si], self.rowlab, self.collab, self.trace, ahead=True)
+            if self.side is not None:
+                torch.cuda.current_stream(self.device).wait_event(self.join)
+            self.si ^= 1
         self.npiv_enqueued += 1
+
+    def first_pick(self, gather=None):
+        """Look-ahead only: the decision for the current table from a classic pick (once per load)."""
+        if not self.lookahead or self.priced:
+            return
+        cur, si = self.npiv_enqueued & 1, self.si
+        self.ops.candidate(self.A[cur], self.b[cur], self.n, self.m_loc, self.ld, self.col0, self.rule,
+                           self.states[si], self.send)
+        (gather or self._all_gather)()
+        self.ops.select(self.gathered, self.world, self.b[cur], self.n, self.rule, self.states[si],
+                        self.colbufs[si])
+        self.priced = True
+
+    def step(self):
+        """One pivot.  Classic: candidate -> all-gather -> select -> update on one stream.
+        Look-ahead: update k on the main stream while candidate -> all-gather -> select price pivot
+        k+1 from the same old table on the side stream; the streams join once per pivot."""
+        self.first_pick()
+        self.phase_local()
+        self.phase_exchange()
+        self.phase_global()
 
     def run(self, pivots: int, check_every: int = 0):
         """Enqueue `pivots` pivots; with check_every > 0 stop early on a terminal status.
@@ -158,7 +244,7 @@ class ShardedTableau:
         return None
 
     def read_state(self) -> N.SpxState:
-        host = self.state.cpu().numpy()
+        host = self.states[self.si if self.lookahead else 0].cpu().numpy()
         st = N.SpxState.from_buffer_copy(host.tobytes())
         return st
 

@@ -102,7 +102,64 @@ class CpuShardOps:
         st.status, st.r, st.c, st.p = N.PIVOT, r, best[1], float(col[r])
         st.slot = (st.npiv + 1) & 1
 
-    def update(self, Ain, Aout, bin_, bout, n, m_loc, ld, col0, state, colbuf, rowlab, collab, trace):
+    # ---- look-ahead halves: price pivot k+1 from table k -------------------------------
+    @staticmethod
+    def _next_local(a, col, r, p, cl, m_loc):
+        """The local columns of the NEXT table (numpy, the update's arithmetic)."""
+        with np.errstate(all="ignore"):
+            new = (a[:, :m_loc] * p - a[r, :m_loc][None, :] * col[:, None]) / p
+            new[r, :] = -a[r, :m_loc] / p
+            if 0 <= cl < m_loc:
+                new[:, cl] = col / p
+                new[r, cl] = 1.0 / p
+        return new
+
+    def ahead_candidate(self, A, bin_, bout, n, m_loc, ld, col0, rule, state, colbuf, send):
+        st = _state(state)
+        msg = send.numpy()
+        hdr = msg[:4].view(np.uint64)
+        if st.status != N.PIVOT:
+            hdr[0] = hdr[1] = hdr[2] = U64_MAX
+            hdr[3] = 1
+            return
+        r, p = st.r, st.p
+        col = colbuf.numpy()[:n + 1]
+        bi = bin_.numpy()[:n]
+        with np.errstate(all="ignore"):
+            nb = (bi * p - bi[r] * col[:n]) / p
+            nb[r] = -bi[r] / p
+        bout.numpy()[:n] = nb
+        new = self._next_local(A.numpy(), col, r, p, st.c - col0, m_loc)
+        neg = np.nonzero(nb < 0)[0]
+        r1 = int(neg[0]) if len(neg) else -1
+        line = new[r1] > 0 if r1 >= 0 else new[n] < 0
+        hit = np.nonzero(line)[0]
+        hdr[2] = np.int64(r1).astype(np.uint64)
+        hdr[3] = 0
+        if len(hit) == 0:
+            hdr[0] = hdr[1] = U64_MAX
+            return
+        j = int(hit[0])
+        hdr[0] = 0
+        hdr[1] = np.uint64(col0 + j)
+        msg[4:4 + n + 1] = new[:, j]
+
+    def ahead_select(self, gathered, world, bnext, n, state_cur, state_next, colbuf_next):
+        cur, nxt = _state(state_cur), _state(state_next)
+        g = gathered.numpy()
+        if cur.status != N.PIVOT or g[0, :4].view(np.uint64)[3] != 0:
+            ctypes.memmove(ctypes.addressof(nxt), ctypes.addressof(cur), ctypes.sizeof(cur))
+            nxt.hint_tag[0] = nxt.hint_tag[1] = -1
+            return
+        ctypes.memmove(ctypes.addressof(nxt), ctypes.addressof(cur), ctypes.sizeof(cur))
+        nxt.npiv = cur.npiv + 1
+        nxt.status = N.PIVOT
+        nxt.hint_tag[0] = nxt.hint_tag[1] = -1
+        # the classic select on the next b, against the advanced pivot counter
+        self.select(gathered, world, bnext, n, 0, state_next, colbuf_next)
+
+    def update(self, Ain, Aout, bin_, bout, n, m_loc, ld, col0, state, colbuf, rowlab, collab, trace,
+               ahead=False):
         st = _state(state)
         if st.status != N.PIVOT:
             return
@@ -120,9 +177,10 @@ class CpuShardOps:
             nb = (bi * p - bi[r] * col[:n]) / p
             nb[r] = -bi[r] / p
         Aout.numpy()[:, :m_loc] = new
-        bout.numpy()[:n] = nb
         rl, cl_ = rowlab.numpy(), collab.numpy()
         rl[cg], cl_[r] = cl_[r], rl[cg]
         if trace is not None:
             trace.numpy()[st.npiv] = (r, cg)
-        st.npiv += 1
+        if not ahead:                 # look-ahead: b and the state belong to the ahead halves
+            bout.numpy()[:n] = nb
+            st.npiv += 1

@@ -338,6 +338,71 @@ def test_every_update_kernel_variant_is_bit_exact(spx, opts):
             L.spx_set_option(k, v)
 
 
+# --------------------------------------------------------------------------- column-sharded flow
+@pytest.mark.parametrize("lookahead", [False, True])
+@pytest.mark.parametrize("world,n,m,kind", [(1, 20, 700, "dense"), (2, 24, 1100, "dense"), (4, 33, 2500, "dense"),
+                                            (3, 12, 1300, "smallint"), (2, 9, 40, "smallint")])
+def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookahead):
+    """The sharded CUDA kernels (candidate / select / update with col0 > 0, and their look-ahead
+    forms) with `world` ranks emulated in one process: the phases of every rank run in lockstep and
+    the all-gather is a device copy.  Trace, labels, b and every body cell equal the oracle's."""
+    from simplex_method_solver_b200 import parallel as P
+    torch = spx.torch
+    if kind == "dense":
+        rows, c = W.dense_lp(n, m, 3)
+    else:
+        rng = np.random.default_rng(5)
+        rows = np.hstack([rng.integers(-3, 4, (n, m)).astype(float), rng.integers(-2, 7, (n, 1)).astype(float)])
+        c = rng.integers(-3, 4, m).astype(float)
+    cap = 40
+    o = oracle.solve(rows, c, max_pivots=cap)
+    shards = [P.ShardedTableau(n, m, r, world, device="cuda", trace_capacity=cap + 8, lookahead=lookahead)
+              for r in range(world)]
+    for sh in shards:
+        sh.load(rows, c, max_pivots=cap)
+
+    def gather_all():
+        torch.cuda.synchronize()                       # emulation only: every rank's send is complete
+        for sh in shards:
+            for g, other in enumerate(shards):
+                sh.gathered[g].copy_(other.send)
+        torch.cuda.synchronize()
+
+    def lockstep(fn_local, fn_global):
+        for sh in shards:
+            fn_local(sh)
+        gather_all()
+        for sh in shards:
+            fn_global(sh)
+
+    if lookahead:
+        def first_local(sh):
+            cur, si = sh.npiv_enqueued & 1, sh.si
+            sh.ops.candidate(sh.A[cur], sh.b[cur], sh.n, sh.m_loc, sh.ld, sh.col0, sh.rule, sh.states[si], sh.send)
+
+        def first_global(sh):
+            cur, si = sh.npiv_enqueued & 1, sh.si
+            sh.ops.select(sh.gathered, sh.world, sh.b[cur], sh.n, sh.rule, sh.states[si], sh.colbufs[si])
+            sh.priced = True
+        lockstep(first_local, first_global)
+    for _ in range(cap + 3):                           # a few steps past the ending: terminal states propagate
+        lockstep(lambda sh: sh.phase_local(), lambda sh: sh.phase_global())
+    body = np.zeros((n + 1, m))
+    for sh in shards:
+        st = sh.sync()
+        assert st.status == o.status and st.npiv == o.npiv, (sh.rank, st.status, st.npiv, o.status, o.npiv)
+        assert sh.trace[: o.npiv].cpu().numpy().tolist() == o.trace.tolist()
+        assert sh.rowlab.cpu().numpy().tolist() == o.rowlab.tolist()
+        assert sh.collab[:n].cpu().numpy().tolist() == o.collab.tolist()
+        body[:, sh.col0: sh.col0 + sh.m_loc] = sh.local_body().cpu().numpy()
+        assert np.array_equal(bits(sh.b_current().cpu().numpy()),
+                              bits(o.table[: n * (m + 1)].reshape(n, m + 1)[:, m].copy()))
+    ob = np.zeros((n + 1, m))
+    ob[:n] = o.table[: n * (m + 1)].reshape(n, m + 1)[:, :m]
+    ob[n] = o.table[n * (m + 1):]
+    assert np.array_equal(bits(body), bits(ob))
+
+
 # --------------------------------------------------------------------------- BASELINE configs
 @pytest.mark.parametrize("lookahead", [False, True])
 def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests, lookahead):

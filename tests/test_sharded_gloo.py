@@ -51,13 +51,14 @@ def test_column_block_alignment():
     assert P.column_block(32768, 3, 8) == (3 * 4096, 4096)
 
 
-def _sharded_worker(rank, world, port, n, m, seed, cap, kind, out):
+def _sharded_worker(rank, world, port, n, m, seed, cap, kind, lookahead, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from cpu_shard_ops import CpuShardOps
         rows, c = _make_lp(n, m, seed, kind)
-        sh = P.ShardedTableau(n, m, rank, world, device="cpu", trace_capacity=cap, ops=CpuShardOps())
+        sh = P.ShardedTableau(n, m, rank, world, device="cpu", trace_capacity=cap, ops=CpuShardOps(),
+                              lookahead=lookahead)
         sh.load(rows, c, max_pivots=cap)
         status, npiv = sh.solve(cap, check_every=5)
         body = sh.local_body().numpy().copy()
@@ -81,11 +82,11 @@ def _make_lp(n, m, seed, kind):
     return np.hstack([A, b[:, None]]), c
 
 
-def _run_world(world, n, m, seed, cap, kind):
+def _run_world(world, n, m, seed, cap, kind, lookahead):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, n, m, seed, cap, kind, out))
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, n, m, seed, cap, kind, lookahead, out))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -96,17 +97,18 @@ def _run_world(world, n, m, seed, cap, kind):
     return got
 
 
+@pytest.mark.parametrize("lookahead", [False, True])
 @pytest.mark.parametrize("world,n,m,kind,seed", [
     (2, 24, 1100, "dense", 3),       # 3 column tiles over 2 ranks: uneven blocks
     (3, 12, 1300, "smallint", 5),    # degenerate ties, phase-1 pivots, error endings
     (2, 9, 40, "smallint", 8),       # fewer tiles than ranks: rank 1 owns no columns
 ])
-def test_sharded_trace_equals_single_process_oracle(world, n, m, kind, seed):
+def test_sharded_trace_equals_single_process_oracle(world, n, m, kind, seed, lookahead):
     import oracle
     cap = 60
     rows, c = _make_lp(n, m, seed, kind)
     o = oracle.solve(rows, c, max_pivots=cap)
-    got = _run_world(world, n, m, seed, cap, kind)
+    got = _run_world(world, n, m, seed, cap, kind, lookahead)
     body = np.zeros((n + 1, m))
     for r in range(world):
         g = got[r]
