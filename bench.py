@@ -174,7 +174,8 @@ def config_dict(ngpu):
     return {"workload": "cfg4: dense LP D(n=16384, m=32768, seed=0), fp64 tableau 4.295 GB (x2 ping-pong)",
             "n": N_ROWS, "m": M_COLS, "cells": cells(N_ROWS, M_COLS),
             "pivots_per_step": PIVOTS_PER_STEP,
-            "parallelism": "single GPU" if ngpu == 1 else f"column-sharded x{ngpu}, one all-gather per pivot",
+            "parallelism": "single GPU" if ngpu == 1 else
+            f"column-sharded x{ngpu}, look-ahead pricing, one candidate exchange per pivot (NVLink peer stores)",
             "l2_policy": "inputs (8.6 GB per pivot) far exceed the 126 MB L2; no flush needed",
             "rule": "reference (first-negative entering, max-negative-ratio leaving)"}
 
@@ -206,6 +207,75 @@ def cpu_baseline_sample(rows, c, gold, budget_s=20.0):
     return {"value": timed / t_used, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"first {timed} pivots (after 1 untimed) of the same 16384x32768 tableau, "
                       f"oracle/spx_oracle.c with OpenMP on {threads} threads"}
+
+
+def batched_leg(dev, rank, world, dist=None, reps=20):
+    """cfg3 of BASELINE.json: 65,536 independent 2-var / 8-constraint LPs, one warp per LP, the batch
+    split contiguously over the ranks with no collective (weak unit: LPs; total work fixed).
+    Returns the dict reported under "batched" (rank 0) — LPs/s resident and end to end."""
+    import torch
+    from simplex_method_solver_b200 import _native as N
+    from simplex_method_solver_b200 import workloads as W
+    from simplex_method_solver_b200.batched import DeviceBatch
+    from simplex_method_solver_b200.parallel import shard_range
+    B, n, m = 65536, 8, 2
+    T, C = W.gui_batch(B, 0)
+    tabs = W.batch_flat(T, C)
+    start, count = shard_range(B, rank, world)
+    pinned = torch.from_numpy(tabs[start:start + count].copy()).pin_memory()
+    db = DeviceBatch(count, n, m, max_pivots=64, trace=True, device=dev)
+    out_x = torch.empty((count, m), dtype=torch.float64).pin_memory()
+    out_st = torch.empty(count, dtype=torch.int32).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident():
+        db.T[:count].copy_(staged)          # device-to-device restore (the solver works in place)
+        db.run()
+
+    def e2e():
+        db.upload(pinned, non_blocking=True)
+        db.run()
+        out_x.copy_(db.x[:count], non_blocking=True)
+        out_st.copy_(db.status[:count], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    staged = pinned.to(dev)
+    ms_res = timed(resident)
+    # the restore copy alone, subtracted so the resident figure is the solver kernel
+    ms_copy = timed(lambda: db.T[:count].copy_(staged))
+    ms_e2e = timed(e2e)
+    res = db.result()
+    piv = torch.tensor([int(res.npiv.sum()), int((res.status == 0).sum())], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(piv)
+    total_piv, n_opt = int(piv[0].item()), int(piv[1].item())
+    assert total_piv == 408212 and n_opt == B, (total_piv, n_opt)     # golden: tests/golden/cfg_digests.json
+    ker_ms = max(ms_res - ms_copy, 1e-6)
+    return {"workload": "cfg3: 65,536 LPs (8 constraints x 2 vars), one warp per LP, split over ranks, no collective",
+            "lps_per_s": B / (ker_ms * 1e-3), "pivots_per_s": total_piv / (ker_ms * 1e-3), "kernel_ms": ker_ms,
+            "e2e_lps_per_s": B / (ms_e2e * 1e-3), "e2e_ms": ms_e2e,
+            "h2d_bytes": int(pinned.numel() * 8), "d2h_bytes": int(out_x.numel() * 8 + out_st.numel() * 4),
+            "northstar_convention_GBps": 16.0 * 26 * total_piv / (ker_ms * 1e-3) / 1e9,
+            "parity": "408,212 pivots, all optimal == golden"}
 
 
 def run_ours(args):
@@ -319,6 +389,7 @@ def run_ours(args):
         e2e_val = P / statistics.mean(e2e_t)
 
         cpu = cpu_baseline_sample(rows, c, gold) if not args.no_cpu_baseline else None
+        batched = batched_leg(dev, 0, 1) if not args.no_batched else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -329,15 +400,20 @@ def run_ours(args):
                     "api": "SimplexMethod(pinned_rows, c).solve(max_pivots=200)"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "hbm_gbs_whole_step": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9,
+            "batched": batched,
             "parity": f"pivot sequence == golden prefix for the first {k} pivots",
         }
         print(json.dumps(line), flush=True)
         return
 
     # ---------------- N > 1: column-sharded, one process per GPU ---------------------------
-    from simplex_method_solver_b200.parallel import ShardedTableau
-    sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
-                        lookahead=not args.no_lookahead)
+    from simplex_method_solver_b200.parallel import PeerShardedTableau, ShardedTableau
+    if args.exchange == "p2p":
+        # C-side look-ahead loop, candidates exchanged by NVLink peer stores (csrc/spx_shard.cu)
+        sh = PeerShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
+    else:
+        sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
+                            lookahead=not args.no_lookahead)
     sh.load(rows, c, max_pivots=need + 64)
     del rows
     for _ in range(args.warmup):
@@ -366,6 +442,11 @@ def run_ours(args):
     assert (tr[:k] == gold[:k]).all(), "sharded pivot sequence differs from the golden prefix"
     value = args.steps * P / (total_ms * 1e-3)
     alg_bytes = 16.0 * cells(N_ROWS, M_COLS)
+    if args.exchange == "p2p":
+        sh.close()
+    del sh
+    torch.cuda.empty_cache()
+    batched = batched_leg(dev, rank, world, dist) if not args.no_batched else None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -378,7 +459,7 @@ def run_ours(args):
                          "peak": peak, "unit": "GB/s per GPU", "peak_source": peak_src,
                          "frac": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9 / world / peak,
                          "traffic": None},
-            "cpu_baseline": None,
+            "cpu_baseline": None, "batched": batched,
             "parity": f"sharded pivot sequence == golden prefix for the first {k} pivots",
         }
         print(json.dumps(line), flush=True)
@@ -393,6 +474,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-pivots-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the cfg3 batched-LP leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: candidate exchange by NVLink peer stores from the C loop (default) or NCCL all-gather")
     ap.add_argument("--no-lookahead", action="store_true",
                     help="classic pick->update order instead of pricing pivot k+1 during update k")
     args = ap.parse_args()

@@ -52,6 +52,7 @@ extern "C" {
 #define SPX_INCORRECT  -1   /* ValueError("incorrect system")                    :88-89   */
 #define SPX_NOCONV     -2   /* ValueError("simplex method does not converge")    :138-139 */
 #define SPX_CAP        -3   /* max_pivots reached; the reference has no cap and cycles    */
+#define SPX_PEER_TIMEOUT -4 /* column-sharded flow: a peer's message did not arrive in 20 s */
 
 /* pivoting rules */
 #define SPX_RULE_REFERENCE 0  /* first-negative entering, max-negative-ratio leaving (the reference) */
@@ -205,9 +206,11 @@ int64_t spx_shard_msg_doubles(int32_t n);
 int spx_shard_candidate(const double *d_A, const double *d_b, int32_t n, int32_t m_loc,
                         int64_t ld_loc, int64_t col0, int32_t rule, int32_t sticky,
                         spx_state *d_state, double *d_send, void *stream);
+/* d_flags/seq: NULL/0 after a library all-gather; with peer mailboxes (below) the LOCAL flag
+ * words flags[parity][nranks] and the exchange number to wait for. */
 int spx_shard_select(const double *d_gathered, int32_t nranks, const double *d_b,
                      int32_t n, int32_t rule, int32_t sticky, spx_state *d_state,
-                     double *d_colbuf, void *stream);
+                     double *d_colbuf, const uint64_t *d_flags, uint64_t seq, void *stream);
 /* ahead != 0: look-ahead mode — the kernel only reads *d_state, skips the b column and the
  * pricing hints (spx_ahead_candidate / spx_ahead_select own them) and still swaps the labels
  * and appends to the trace. */
@@ -231,7 +234,43 @@ int spx_ahead_candidate(const double *d_A, const double *d_bin, double *d_bout, 
                         const double *d_colbuf, double *d_send, void *stream);
 int spx_ahead_select(const double *d_gathered, int32_t nranks, const double *d_bnext, int32_t n,
                      const spx_state *d_state_cur, spx_state *d_state_next, double *d_colbuf_next,
-                     void *stream);
+                     const uint64_t *d_flags, uint64_t seq, void *stream);
+
+/* ---- the exchange over NVLink peer memory (no library collective on the data path) -------
+ * Each rank owns a MAILBOX  gathered[2][nranks][spx_shard_msg_doubles(n)] | flags[2][nranks]
+ * (spx_mailbox_bytes, zero-initialised, allocated with spx_device_alloc so that it can be
+ * exported over CUDA IPC to the other ranks' processes).  spx_peer_push stores this rank's
+ * message into EVERY rank's mailbox (one CTA per destination, 128-bit stores through NVLink)
+ * and release-stores `seq` into the destination's flag word; the select kernels acquire-poll
+ * their local flags (20 s timeout -> SPX_PEER_TIMEOUT).  parity = seq & 1. */
+typedef struct spx_shard spx_shard;
+int     spx_device_alloc(void **d_ptr, int64_t bytes);
+int     spx_device_free(void *d_ptr);
+int     spx_ipc_handle_bytes(void);
+int     spx_ipc_export(void *d_ptr, void *handle_out);
+int     spx_ipc_import(const void *handle, void **d_ptr);
+int     spx_ipc_close(void *d_ptr);
+int64_t spx_mailbox_bytes(int32_t n, int32_t nranks);
+int     spx_peer_push(const double *d_send, int32_t n, int32_t rank, int32_t nranks, int32_t parity,
+                      uint64_t seq, void *const *mailboxes, void *stream);
+
+/* The whole sharded look-ahead loop behind one handle, enqueued from C (no Python and no
+ * collective library per pivot): spx_shard_enqueue(h, K) enqueues K pivots — update k on
+ * `stream`, pricing of pivot k+1 (next b, local candidate, peer push, select) on the handle's
+ * high-priority side stream — and returns; every rank must enqueue the same K.
+ *   d_state2  : spx_state[2] (element 0 initialised by spx_init_state)
+ *   d_colbuf2 : 2 * spx_colbuf_doubles(n) doubles
+ *   mailboxes : nranks device pointers valid in THIS process ([rank] = the local mailbox)
+ * spx_shard_read synchronises `stream`, returns the current (already priced) state and the
+ * index (0/1) of the ping-pong buffer that holds the current table. */
+int spx_shard_open(spx_shard **out, int32_t rank, int32_t nranks, int32_t n, int32_t m_loc, int64_t ld_loc,
+                   int64_t col0, int32_t rule, double *d_A0, double *d_A1, double *d_b0, double *d_b1,
+                   spx_state *d_state2, double *d_colbuf2, int32_t *d_rowlab, int32_t *d_collab,
+                   int32_t *d_trace, double *d_send, void *const *mailboxes);
+int spx_shard_reset(spx_shard *h);
+int spx_shard_enqueue(spx_shard *h, int64_t pivots, void *stream);
+int spx_shard_read(spx_shard *h, spx_state *h_state, int32_t *cur_buffer, void *stream);
+int spx_shard_close(spx_shard *h);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libspx_b200.so")
 
 ABI_VERSION = 2
-PIVOT, OPTIMAL, INCORRECT, NOCONV, CAP = 1, 0, -1, -2, -3
+PIVOT, OPTIMAL, INCORRECT, NOCONV, CAP, PEER_TIMEOUT = 1, 0, -1, -2, -3, -4
 RULE_REFERENCE, RULE_DANTZIG = 0, 1
 OPT_UPDATE_KERNEL, OPT_TILED_MIN_BLOCKS, OPT_PIPE_ORDER, OPT_PIPE_GRID = 1, 2, 3, 4
 RULES = {"reference": RULE_REFERENCE, "bland": RULE_REFERENCE, "dantzig": RULE_DANTZIG}
@@ -75,11 +75,25 @@ SIGNATURES = {
     "spx_batched_max_cells": (_i64, []),
     "spx_shard_msg_doubles": (_i64, [_i32]),
     "spx_shard_candidate": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
-    "spx_shard_select": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "spx_shard_select": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, ctypes.c_uint64, _vp]),
     "spx_shard_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp,
                                         _vp, _i32, _vp]),
     "spx_ahead_candidate": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _vp]),
-    "spx_ahead_select": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "spx_ahead_select": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, ctypes.c_uint64, _vp]),
+    "spx_device_alloc": (ctypes.c_int, [ctypes.POINTER(_vp), _i64]),
+    "spx_device_free": (ctypes.c_int, [_vp]),
+    "spx_ipc_handle_bytes": (ctypes.c_int, []),
+    "spx_ipc_export": (ctypes.c_int, [_vp, _vp]),
+    "spx_ipc_import": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "spx_ipc_close": (ctypes.c_int, [_vp]),
+    "spx_mailbox_bytes": (_i64, [_i32, _i32]),
+    "spx_peer_push": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, ctypes.c_uint64, ctypes.POINTER(_vp), _vp]),
+    "spx_shard_open": (ctypes.c_int, [ctypes.POINTER(_vp), _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _vp, _vp,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
+    "spx_shard_reset": (ctypes.c_int, [_vp]),
+    "spx_shard_enqueue": (ctypes.c_int, [_vp, _i64, _vp]),
+    "spx_shard_read": (ctypes.c_int, [_vp, _vp, _pi32, _vp]),
+    "spx_shard_close": (ctypes.c_int, [_vp]),
 }
 
 _lib = None

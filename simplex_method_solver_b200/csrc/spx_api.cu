@@ -19,13 +19,13 @@ cudaError_t pick(const double *, const double *, int, int, int64_t, int, int, sp
 cudaError_t shard_candidate(const double *, const double *, int, int, int64_t, int64_t, int, int,
                             const spx_state *, double *, cudaStream_t);
 cudaError_t shard_select(const double *, int, const double *, int, int, spx_state *, double *,
-                         cudaStream_t);
+                         const unsigned long long *, unsigned long long, cudaStream_t);
 cudaError_t update(const double *, double *, const double *, double *, int, int, int64_t, int64_t,
                    spx_state *, const double *, int32_t *, int32_t *, int32_t *, int, cudaStream_t);
 cudaError_t ahead_candidate(const double *, const double *, double *, int, int, int64_t, int64_t, int,
                             const spx_state *, const double *, double *, cudaStream_t);
 cudaError_t ahead_select(const double *, int, const double *, int, const spx_state *, spx_state *,
-                         double *, cudaStream_t);
+                         double *, const unsigned long long *, unsigned long long, cudaStream_t);
 cudaError_t extract(const double *, int, int, const int32_t *, const double *, double *, double *,
                     cudaStream_t);
 int64_t get_option(int);
@@ -346,8 +346,8 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
                 if (check(cudaStreamWaitEvent(sc->side, sc->fork, 0), "fork wait")) return -1;
                 if (check(spx_launch::ahead_candidate(A[cur], b[cur], b[cur ^ 1], n, m, ld, 0, rule, S[si], C[si],
                                                       w.msg, sc->side), "candidate launch")) return -1;
-                if (check(spx_launch::ahead_select(w.msg, 1, b[cur ^ 1], n, S[si], S[si ^ 1], C[si ^ 1], sc->side),
-                          "select launch")) return -1;
+                if (check(spx_launch::ahead_select(w.msg, 1, b[cur ^ 1], n, S[si], S[si ^ 1], C[si ^ 1], nullptr, 0,
+                                                   sc->side), "select launch")) return -1;
                 if (check(cudaEventRecord(sc->join, sc->side), "join")) return -1;
                 if (check(spx_launch::update(A[cur], A[cur ^ 1], b[cur], b[cur ^ 1], n, m, ld, 0, S[si], C[si],
                                              d_rowlab, d_collab, d_trace, 1, s), "update launch")) return -1;
@@ -409,11 +409,13 @@ int spx_shard_candidate(const double *d_A, const double *d_b, int32_t n, int32_t
 }
 
 int spx_shard_select(const double *d_gathered, int32_t nranks, const double *d_b, int32_t n, int32_t rule,
-                     int32_t sticky, spx_state *d_state, double *d_colbuf, void *stream) {
+                     int32_t sticky, spx_state *d_state, double *d_colbuf, const uint64_t *d_flags,
+                     uint64_t seq, void *stream) {
     (void)rule;
     SPX_REQUIRE(d_gathered && d_b && d_state && d_colbuf && nranks >= 1 && n >= 1,
                 "spx_shard_select: bad arguments");
     return check(spx_launch::shard_select(d_gathered, nranks, d_b, n, sticky, d_state, d_colbuf,
+                                          reinterpret_cast<const unsigned long long *>(d_flags), seq,
                                           as_stream(stream)), "select launch");
 }
 
@@ -430,11 +432,12 @@ int spx_ahead_candidate(const double *d_A, const double *d_bin, double *d_bout, 
 
 int spx_ahead_select(const double *d_gathered, int32_t nranks, const double *d_bnext, int32_t n,
                      const spx_state *d_state_cur, spx_state *d_state_next, double *d_colbuf_next,
-                     void *stream) {
+                     const uint64_t *d_flags, uint64_t seq, void *stream) {
     SPX_REQUIRE(d_gathered && d_bnext && d_state_cur && d_state_next && d_colbuf_next && nranks >= 1 && n >= 1 &&
                 d_state_cur != d_state_next, "spx_ahead_select: bad arguments");
     return check(spx_launch::ahead_select(d_gathered, nranks, d_bnext, n, d_state_cur, d_state_next,
-                                          d_colbuf_next, as_stream(stream)), "select launch");
+                                          d_colbuf_next, reinterpret_cast<const unsigned long long *>(d_flags),
+                                          seq, as_stream(stream)), "select launch");
 }
 
 } // extern "C"

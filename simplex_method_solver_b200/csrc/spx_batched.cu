@@ -42,7 +42,30 @@ __device__ __forceinline__ int warp_first_index(int len, int lane, F pred) {
     return SPX_NONE;
 }
 
-__global__ void __launch_bounds__(256)
+// Cross-lane finish of the ratio scan.  Every lane holds the fold of its own rows; the decision of
+// ratio_decide() over the union is taken with redux/ballot instead of a shuffle tree of structs.
+__device__ __forceinline__ int warp_ratio_decide(const Ratio &q, bool my_elig_nan, int lane) {
+    const unsigned full = 0xffffffffu;
+    const int elig = __reduce_min_sync(full, q.elig_row);
+    if (elig == SPX_NONE) return -1;                                       // first_try still True
+    if (__ballot_sync(full, q.elig_row == elig && my_elig_nan)) return elig;   // NaN min_val is never replaced
+    const bool has_neg = q.neg_row >= 0;
+    if (__ballot_sync(full, has_neg)) {
+        // largest negative ratio: max of the order-preserving 64-bit image, 32 bits at a time
+        const unsigned long long key = has_neg ? orderable(q.neg_val) : 0ull;
+        const unsigned hi = (unsigned)(key >> 32);
+        const unsigned mhi = __reduce_max_sync(full, hi);
+        const bool c1 = has_neg && hi == mhi;
+        const unsigned lo = c1 ? (unsigned)key : 0u;
+        const unsigned mlo = __reduce_max_sync(full, lo);
+        const bool c2 = c1 && lo == mlo;
+        return __reduce_max_sync(full, c2 ? q.neg_row : -1);               // ties -> highest row (:133, '<=')
+    }
+    const int zero = __reduce_min_sync(full, q.zero_row);
+    return (zero != SPX_NONE) ? zero : -1;                                 // first zero ratio, else min_val > 0
+}
+
+__global__ void __launch_bounds__(256, 4)
 batched_kernel(BatchedArgs a, int warps_per_cta, int warp_doubles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n, m = a.m, w1 = m + 1;
@@ -116,35 +139,37 @@ batched_kernel(BatchedArgs a, int warps_per_cta, int warp_doubles) {
                           return v < 0.0 && orderable(v) == best; });
             }
             if (c == SPX_NONE) { status = SPX_OPTIMAL; break; }                   // :101-103
-            // ---- K2: the ratio scan (:107-136) as a warp reduction
+            // ---- K2: the ratio scan (:107-136): lane-local fold, then ballots / redux across lanes
             Ratio q = ratio_identity();
-            for (int i = lane; i < n; i += 32) ratio_accumulate(q, i, cur[i * w1 + c], cur[i * w1 + m]);
-            q = warp_ratio_reduce(q);
-            bool elig_nan = false;
-            if (q.elig_row != SPX_NONE) {
-                const double v = __ddiv_rn(cur[q.elig_row * w1 + m], cur[q.elig_row * w1 + c]);
-                elig_nan = (v != v);
+            bool my_elig_nan = false;                    // is the ratio of MY first eligible row NaN?
+            for (int i = lane; i < n; i += 32) {
+                const double a_ic = cur[i * w1 + c], b_i = cur[i * w1 + m];
+                const bool first = (q.elig_row == SPX_NONE);
+                const bool is_nan = ratio_accumulate(q, i, a_ic, b_i);
+                if (first && q.elig_row != SPX_NONE) my_elig_nan = is_nan;
             }
-            r = ratio_decide(q, elig_nan);
+            r = warp_ratio_decide(q, my_elig_nan, lane);
             if (r < 0) { status = SPX_NOCONV; break; }                            // :138-139
         }
         if (npiv >= a.max_pivots) { status = SPX_CAP; break; }
         if (trace && lane == 0) { trace[2 * npiv] = r; trace[2 * npiv + 1] = c; }
 
-        // ---- K3: out-of-place pivot (:149-177), all reads from `cur`
+        // ---- K3: out-of-place pivot (:149-177), all reads from `cur`; the four cell kinds
+        // (:156 pivot row, :160 pivot column, :163 pivot cell, :173-175 the rest) differ only in
+        // the numerator, so one division by the pivot serves them all without divergence
         const double p = cur[r * w1 + c];
+        const PivotDiv d = pivot_div_prepare(p);
         const double *prow = cur + r * w1;
         for (int k = lane; k < cells; k += 32) {
             const int i = cell_i[k], j = cell_j[k];
             const double t = cur[k];
-            double o;
-            if (i == r) {
-                o = (j == c) ? pivot_cell_update(p) : pivot_row_update(t, p);     // :163, :156
-            } else {
-                const double ci = cur[i * w1 + c];
-                o = (j == c) ? pivot_col_update(ci, p) : cell_update(t, p, prow[j], ci);   // :160, :173-175
-            }
-            nxt[k] = o;
+            const double ci = cur[i * w1 + c];
+            const bool pr = (i == r), pc = (j == c);
+            double num = __dsub_rn(__dmul_rn(t, p), __dmul_rn(prow[j], ci));
+            num = pc ? ci : num;
+            num = pr ? -t : num;
+            num = (pr && pc) ? 1.0 : num;
+            nxt[k] = pivot_div(num, d);
         }
         if (lane == 0) { const int32_t t = rl[c]; rl[c] = cl[r]; cl[r] = t; }     // :152
         __syncwarp();

@@ -84,6 +84,33 @@ __device__ __forceinline__ Ratio block_ratio_reduce(Ratio q, Scratch &s) {
     return out;
 }
 
+// ---- peer mailboxes (column-sharded flow over NVLink peer memory) ------------------
+// Every rank's candidate message is stored by its owner straight into each peer's mailbox
+// (peer_push_kernel, spx_shard.cu) followed by a release-store of the exchange number into the
+// peer's flag word; the select kernels acquire-poll their LOCAL flags before reading.  Returns
+// false on timeout (a peer died): the caller reports SPX_PEER_TIMEOUT instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ bool wait_flags(const unsigned long long *flags, int nranks, unsigned long long seq) {
+    bool ok = true;
+    if (flags != nullptr && (int)threadIdx.x < nranks) {
+        const unsigned long long *f = flags + threadIdx.x;
+        const unsigned long long t0 = global_timer_ns();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= seq) break;
+            if (global_timer_ns() - t0 > 20000000000ull) { ok = false; break; }     // 20 s
+            __nanosleep(100);
+        }
+    }
+    return __syncthreads_or(ok ? 0 : 1) == 0;
+}
+
 struct IsNeg { __device__ bool operator()(double v) const { return v < 0.0; } };   // :74, :96
 struct IsPos { __device__ bool operator()(double v) const { return v > 0.0; } };   // :83
 
@@ -286,11 +313,15 @@ shard_candidate_kernel(const double *__restrict__ A, const double *__restrict__ 
 
 // global half of K1 + K2 from the gathered messages of all ranks
 __global__ void __launch_bounds__(PICK_THREADS, 1)
-shard_select_kernel(const double *__restrict__ gathered, int nranks, int64_t msg_doubles,
+shard_select_kernel(const double *gathered, int nranks, int64_t msg_doubles,
                     const double *__restrict__ b, int n, int sticky, spx_state *st,
-                    double *__restrict__ colbuf) {
+                    double *__restrict__ colbuf, const unsigned long long *flags, unsigned long long seq) {
     __shared__ Scratch s;
     if (sticky && st->status != SPX_PIVOT) return;
+    if (!wait_flags(flags, nranks, seq)) {
+        if (threadIdx.x == 0) st->status = SPX_PEER_TIMEOUT;
+        return;
+    }
     // every thread scans the (few) headers: lexicographic min of (key_hi, key_lo)
     unsigned long long bh = ~0ull, bl = ~0ull; int win = -1;
     for (int g = 0; g < nranks; ++g) {
@@ -425,10 +456,15 @@ ahead_candidate_kernel(const double *__restrict__ A, const double *__restrict__ 
 // global half: min key over the ranks' messages, ratio test on the winning column with the next b,
 // next state written to st_next (st_cur is still being read by the running update)
 __global__ void __launch_bounds__(AHEAD_THREADS, 3)
-ahead_select_kernel(const double *__restrict__ gathered, int nranks, int64_t msg_doubles,
+ahead_select_kernel(const double *gathered, int nranks, int64_t msg_doubles,
                     const double *__restrict__ bnext, int n, const spx_state *__restrict__ st_cur,
-                    spx_state *__restrict__ st_next, double *__restrict__ colbuf_next) {
+                    spx_state *__restrict__ st_next, double *__restrict__ colbuf_next,
+                    const unsigned long long *flags, unsigned long long seq) {
     __shared__ Scratch s;
+    if (!wait_flags(flags, nranks, seq)) {
+        if (threadIdx.x == 0) { *st_next = *st_cur; st_next->status = SPX_PEER_TIMEOUT; }
+        return;
+    }
     const unsigned long long *h0 = reinterpret_cast<const unsigned long long *>(gathered);
     if (st_cur->status != SPX_PIVOT || h0[3] != 0ull) {
         if (threadIdx.x == 0) { *st_next = *st_cur; st_next->hint_tag[0] = st_next->hint_tag[1] = -1; }
@@ -486,9 +522,10 @@ cudaError_t shard_candidate(const double *A, const double *b, int n, int m_loc, 
 }
 
 cudaError_t shard_select(const double *gathered, int nranks, const double *b, int n, int sticky,
-                         spx_state *st, double *colbuf, cudaStream_t stream) {
+                         spx_state *st, double *colbuf, const unsigned long long *flags,
+                         unsigned long long seq, cudaStream_t stream) {
     shard_select_kernel<<<1, PICK_THREADS, 0, stream>>>(gathered, nranks, shard_msg_doubles(n), b,
-                                                        n, sticky, st, colbuf);
+                                                        n, sticky, st, colbuf, flags, seq);
     spx_host::count_launch();
     return cudaGetLastError();
 }
@@ -504,9 +541,9 @@ cudaError_t ahead_candidate(const double *A, const double *bin, double *bout, in
 
 cudaError_t ahead_select(const double *gathered, int nranks, const double *bnext, int n,
                          const spx_state *st_cur, spx_state *st_next, double *colbuf_next,
-                         cudaStream_t stream) {
+                         const unsigned long long *flags, unsigned long long seq, cudaStream_t stream) {
     ahead_select_kernel<<<1, AHEAD_THREADS, 0, stream>>>(gathered, nranks, shard_msg_doubles(n), bnext, n,
-                                                         st_cur, st_next, colbuf_next);
+                                                         st_cur, st_next, colbuf_next, flags, seq);
     spx_host::count_launch();
     return cudaGetLastError();
 }

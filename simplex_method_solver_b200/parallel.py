@@ -64,6 +64,77 @@ def msg_doubles(n: int) -> int:
     return (MSG_HEADER + n + 1 + 15) // 16 * 16
 
 
+def _p(x):
+    """Device pointer of a tensor, or the integer address itself."""
+    return x if isinstance(x, int) or x is None else x.data_ptr()
+
+
+class PeerMailboxes:
+    """Every rank's mailbox mapped into this process (CUDA IPC): the NVLink exchange of the sharded flow.
+
+    Layout per rank (csrc/spx_shard.cu): gathered[2][world][msg] | flags[2][world].  The local box is
+    cudaMalloc'ed by the library (exportable), the peers' boxes are opened from handles exchanged
+    once through torch.distributed — plumbing only; the per-pivot exchange is spx_peer_push.
+    """
+
+    def __init__(self, n: int, rank: int, world: int, device, group=None, local_only_ptrs=None):
+        L = N.lib()
+        self.n, self.rank, self.world = int(n), int(rank), int(world)
+        self.device = torch.device(device)
+        self.msgd = int(L.spx_shard_msg_doubles(self.n))
+        self.bytes = int(L.spx_mailbox_bytes(self.n, self.world))
+        self.flags_offset = (2 * self.world * self.msgd * 8 + 127) // 128 * 128
+        self._opened = []
+        with torch.cuda.device(self.device):
+            local = ctypes.c_void_p()
+            N.call("spx_device_alloc", ctypes.byref(local), self.bytes)
+            self.local = int(local.value)
+            ptrs = [None] * self.world
+            ptrs[self.rank] = self.local
+            if local_only_ptrs is not None:            # several ranks emulated inside one process (tests)
+                self._shared = local_only_ptrs
+                local_only_ptrs[self.rank] = self.local
+                self.ptrs = None
+                return
+            if self.world > 1:
+                hb = int(L.spx_ipc_handle_bytes())
+                buf = (ctypes.c_ubyte * hb)()
+                N.call("spx_ipc_export", self.local, buf)
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(buf), group=group)
+                for g in range(self.world):
+                    if g == self.rank:
+                        continue
+                    hbuf = (ctypes.c_ubyte * hb).from_buffer_copy(handles[g])
+                    q = ctypes.c_void_p()
+                    N.call("spx_ipc_import", hbuf, ctypes.byref(q))
+                    ptrs[g] = int(q.value)
+                    self._opened.append(int(q.value))
+            self.ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+
+    def finalize_shared(self):
+        """Emulation only: call once every emulated rank has allocated its box."""
+        self.ptrs = (ctypes.c_void_p * self.world)(*self._shared)
+
+    def gathered_ptr(self, parity: int) -> int:
+        return self.local + parity * self.world * self.msgd * 8
+
+    def flags_ptr(self, parity: int) -> int:
+        return self.local + self.flags_offset + parity * self.world * 8
+
+    def close(self, group=None):
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for q in self._opened:
+                N.call("spx_ipc_close", q)
+            self._opened = []
+            if self.world > 1 and dist.is_initialized() and self.ptrs is not None and getattr(self, "_shared", None) is None:
+                dist.barrier(group=group)              # nobody frees a box a peer still has mapped
+            if self.local:
+                N.call("spx_device_free", self.local)
+                self.local = 0
+
+
 class CudaShardOps:
     """The three per-pivot kernels of the sharded flow, through the C ABI."""
 
@@ -87,9 +158,12 @@ class CudaShardOps:
         N.call("spx_shard_candidate", A.data_ptr(), b.data_ptr(), n, m_loc, ld, col0, rule, 1,
                state.data_ptr(), send.data_ptr(), self._stream())
 
-    def select(self, gathered, world, b, n, rule, state, colbuf):
-        N.call("spx_shard_select", gathered.data_ptr(), world, b.data_ptr(), n, rule, 1,
-               state.data_ptr(), colbuf.data_ptr(), self._stream())
+    def select(self, gathered, world, b, n, rule, state, colbuf, flags=None, seq=0):
+        N.call("spx_shard_select", _p(gathered), world, b.data_ptr(), n, rule, 1,
+               state.data_ptr(), colbuf.data_ptr(), flags, seq, self._stream())
+
+    def push(self, send, n, rank, world, parity, seq, ptrs):
+        N.call("spx_peer_push", send.data_ptr(), n, rank, world, parity, seq, ptrs, self._stream())
 
     def update(self, Ain, Aout, bin_, bout, n, m_loc, ld, col0, state, colbuf, rowlab, collab, trace,
                ahead=False):
@@ -101,21 +175,24 @@ class CudaShardOps:
         N.call("spx_ahead_candidate", A.data_ptr(), bin_.data_ptr(), bout.data_ptr(), n, m_loc, ld, col0,
                rule, state.data_ptr(), colbuf.data_ptr(), send.data_ptr(), self._stream())
 
-    def ahead_select(self, gathered, world, bnext, n, state_cur, state_next, colbuf_next):
-        N.call("spx_ahead_select", gathered.data_ptr(), world, bnext.data_ptr(), n, state_cur.data_ptr(),
-               state_next.data_ptr(), colbuf_next.data_ptr(), self._stream())
+    def ahead_select(self, gathered, world, bnext, n, state_cur, state_next, colbuf_next, flags=None, seq=0):
+        N.call("spx_ahead_select", _p(gathered), world, bnext.data_ptr(), n, state_cur.data_ptr(),
+               state_next.data_ptr(), colbuf_next.data_ptr(), flags, seq, self._stream())
 
 
 class ShardedTableau:
     """One rank's share of a column-sharded tableau plus the replicated pieces."""
 
     def __init__(self, n: int, m: int, rank: int, world: int, device, trace_capacity: int = 0,
-                 group=None, ops=None, rule: int = N.RULE_REFERENCE, lookahead: bool = False):
+                 group=None, ops=None, rule: int = N.RULE_REFERENCE, lookahead: bool = False,
+                 mailboxes: Optional["PeerMailboxes"] = None):
         self.n, self.m, self.rank, self.world = int(n), int(m), int(rank), int(world)
         self.device = torch.device(device)
         self.group = group
         self.rule = rule
         self.lookahead = bool(lookahead)
+        self.mailboxes = mailboxes     # None: the exchange is a torch.distributed all-gather
+        self.seq = 0                   # exchanges issued (mailbox mode); parity = seq & 1
         self.ops = ops if ops is not None else CudaShardOps(self.device)
         self.col0, self.m_loc = column_block(self.m, self.rank, self.world)
         self.ld = max(16, (self.m_loc + 15) // 16 * 16)
@@ -178,21 +255,36 @@ class ShardedTableau:
             self.ops.ahead_candidate(self.A[cur], self.b[cur], self.b[cur ^ 1], self.n, self.m_loc, self.ld,
                                      self.col0, self.rule, S[si], C[si], self.send)
 
+    def _exchange(self, gather=None):
+        if self.mailboxes is not None:       # NVLink peer stores + flags, no collective
+            self.seq += 1
+            self.ops.push(self.send, self.n, self.rank, self.world, self.seq & 1, self.seq, self.mailboxes.ptrs)
+        else:
+            (gather or self._all_gather)()
+
+    def _gathered_and_flags(self):
+        if self.mailboxes is None:
+            return self.gathered, None, 0
+        par = self.seq & 1
+        return self.mailboxes.gathered_ptr(par), self.mailboxes.flags_ptr(par), self.seq
+
     def phase_exchange(self, gather=None):
         with (self._on_side() if self.lookahead else contextlib.nullcontext()):
-            (gather or self._all_gather)()
+            self._exchange(gather)
 
     def phase_global(self):
         cur = self.npiv_enqueued & 1
+        gathered, flags, seq = self._gathered_and_flags()
         if not self.lookahead:
-            self.ops.select(self.gathered, self.world, self.b[cur], self.n, self.rule, self.state, self.colbuf)
+            self.ops.select(gathered, self.world, self.b[cur], self.n, self.rule, self.state, self.colbuf,
+                            flags, seq)
             self.ops.update(self.A[cur], self.A[cur ^ 1], self.b[cur], self.b[cur ^ 1], self.n, self.m_loc,
                             self.ld, self.col0, self.state, self.colbuf, self.rowlab, self.collab, self.trace)
         else:
             S, C, si = self.states, self.colbufs, self.si
             with self._on_side():
-                self.ops.ahead_select(self.gathered, self.world, self.b[cur ^ 1], self.n, S[si], S[si ^ 1],
-                                      C[si ^ 1])
+                self.ops.ahead_select(gathered, self.world, self.b[cur ^ 1], self.n, S[si], S[si ^ 1],
+                                      C[si ^ 1], flags, seq)
                 if self.side is not None:
                     self.join.record(self.side)
             # the streaming update of pivot k: main stream, concurrent with the pricing above
@@ -210,9 +302,10 @@ class ShardedTableau:
         cur, si = self.npiv_enqueued & 1, self.si
         self.ops.candidate(self.A[cur], self.b[cur], self.n, self.m_loc, self.ld, self.col0, self.rule,
                            self.states[si], self.send)
-        (gather or self._all_gather)()
-        self.ops.select(self.gathered, self.world, self.b[cur], self.n, self.rule, self.states[si],
-                        self.colbufs[si])
+        self._exchange(gather)
+        gathered, flags, seq = self._gathered_and_flags()
+        self.ops.select(gathered, self.world, self.b[cur], self.n, self.rule, self.states[si],
+                        self.colbufs[si], flags, seq)
         self.priced = True
 
     def step(self):
@@ -282,6 +375,87 @@ class ShardedTableau:
     def b_current(self) -> torch.Tensor:
         self.sync()
         return self.b[self.npiv_enqueued & 1, : self.n]
+
+
+class PeerShardedTableau(ShardedTableau):
+    """The sharded look-ahead loop enqueued from C (spx_shard_* handle, csrc/spx_shard.cu): per pivot
+    no Python, no collective library — update k on the main stream, next b / candidate / NVLink peer
+    push / select for pivot k+1 on the handle's side stream."""
+
+    def __init__(self, n: int, m: int, rank: int, world: int, device, trace_capacity: int = 0,
+                 group=None, rule: int = N.RULE_REFERENCE):
+        super().__init__(n, m, rank, world, device, trace_capacity=trace_capacity, group=group, rule=rule,
+                         lookahead=False)
+        L = N.lib()
+        dev = self.device
+        self.lookahead = True
+        # the handle wants spx_state[2] and colbuf[2] contiguous
+        self.state2 = torch.zeros(2 * ctypes.sizeof(N.SpxState) // 8, dtype=torch.int64, device=dev)
+        half = self.state2.numel() // 2
+        self.states = [self.state2[:half], self.state2[half:]]
+        self.state = self.states[0]
+        cb = int(L.spx_colbuf_doubles(self.n))
+        self.colbuf2 = torch.zeros(2 * cb, dtype=torch.float64, device=dev)
+        self.colbufs = [self.colbuf2[:cb], self.colbuf2[cb:]]
+        self.colbuf = self.colbufs[0]
+        self.mailboxes = PeerMailboxes(self.n, rank, world, dev, group=group)
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            N.call("spx_shard_open", ctypes.byref(self.handle), rank, world, self.n, self.m_loc, self.ld, self.col0,
+                   rule, self.A[0].data_ptr(), self.A[1].data_ptr(), self.b[0].data_ptr(), self.b[1].data_ptr(),
+                   self.state2.data_ptr(), self.colbuf2.data_ptr(), self.rowlab.data_ptr(), self.collab.data_ptr(),
+                   N.ptr(self.trace), self.send.data_ptr(), self.mailboxes.ptrs)
+        self._cur = 0
+
+    def load(self, rows, function, max_pivots: int):
+        super().load(rows, function, max_pivots)
+        N.call("spx_shard_reset", self.handle)
+        self._cur = 0
+
+    def step(self):
+        self.run(1)
+
+    def run(self, pivots: int, check_every: int = 0):
+        done = 0
+        while done < pivots:
+            k = pivots - done if check_every <= 0 else min(check_every, pivots - done)
+            with torch.cuda.device(self.device):
+                N.call("spx_shard_enqueue", self.handle, k, torch.cuda.current_stream(self.device).cuda_stream)
+            done += k
+            if check_every > 0:
+                st = self.read_state()
+                if st.status != N.PIVOT:
+                    return st
+        return None
+
+    def read_state(self) -> N.SpxState:
+        st = N.SpxState()
+        cur = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            N.call("spx_shard_read", self.handle, ctypes.byref(st), ctypes.byref(cur),
+                   torch.cuda.current_stream(self.device).cuda_stream)
+        self._cur = int(cur.value)
+        self.npiv_enqueued = int(st.npiv) if st.status != N.PIVOT else self.npiv_enqueued
+        return st
+
+    def sync(self) -> N.SpxState:
+        st = self.read_state()
+        self.npiv_enqueued = int(st.npiv)
+        return st
+
+    def solve(self, max_pivots: int, check_every: int = 64):
+        while True:
+            st = self.run(check_every, check_every=check_every)
+            if st is None:
+                st = self.read_state()
+            if st.status != N.PIVOT or st.npiv >= max_pivots:
+                return int(st.status), int(st.npiv)
+
+    def close(self):
+        if self.handle:
+            N.call("spx_shard_close", self.handle)
+            self.handle = ctypes.c_void_p()
+        self.mailboxes.close(group=self.group)
 
 
 def solve_batched_sharded(tables: np.ndarray, n: int, m: int, max_pivots: int = 64, rule: str = "reference",

@@ -57,7 +57,7 @@ class CpuShardOps:
         hdr[1] = np.uint64(col0 + j)
         msg[4:4 + n + 1] = a[:, j]
 
-    def select(self, gathered, world, b, n, rule, state, colbuf):
+    def select(self, gathered, world, b, n, rule, state, colbuf, flags=None, seq=0):
         st = _state(state)
         if st.status != N.PIVOT:
             return
@@ -144,7 +144,7 @@ class CpuShardOps:
         hdr[1] = np.uint64(col0 + j)
         msg[4:4 + n + 1] = new[:, j]
 
-    def ahead_select(self, gathered, world, bnext, n, state_cur, state_next, colbuf_next):
+    def ahead_select(self, gathered, world, bnext, n, state_cur, state_next, colbuf_next, flags=None, seq=0):
         cur, nxt = _state(state_cur), _state(state_next)
         g = gathered.numpy()
         if cur.status != N.PIVOT or g[0, :4].view(np.uint64)[3] != 0:

@@ -339,10 +339,11 @@ def test_every_update_kernel_variant_is_bit_exact(spx, opts):
 
 
 # --------------------------------------------------------------------------- column-sharded flow
+@pytest.mark.parametrize("exchange", ["copy", "mailbox"])
 @pytest.mark.parametrize("lookahead", [False, True])
 @pytest.mark.parametrize("world,n,m,kind", [(1, 20, 700, "dense"), (2, 24, 1100, "dense"), (4, 33, 2500, "dense"),
                                             (3, 12, 1300, "smallint"), (2, 9, 40, "smallint")])
-def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookahead):
+def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookahead, exchange):
     """The sharded CUDA kernels (candidate / select / update with col0 > 0, and their look-ahead
     forms) with `world` ranks emulated in one process: the phases of every rank run in lockstep and
     the all-gather is a device copy.  Trace, labels, b and every body cell equal the oracle's."""
@@ -356,16 +357,26 @@ def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookah
         c = rng.integers(-3, 4, m).astype(float)
     cap = 40
     o = oracle.solve(rows, c, max_pivots=cap)
-    shards = [P.ShardedTableau(n, m, r, world, device="cuda", trace_capacity=cap + 8, lookahead=lookahead)
-              for r in range(world)]
+    boxes = None
+    if exchange == "mailbox":                          # NVLink-style peer stores + flags, all boxes in one process
+        shared = [None] * world
+        boxes = [P.PeerMailboxes(n, r, world, "cuda", local_only_ptrs=shared) for r in range(world)]
+        for bx in boxes:
+            bx.finalize_shared()
+    shards = [P.ShardedTableau(n, m, r, world, device="cuda", trace_capacity=cap + 8, lookahead=lookahead,
+                               mailboxes=boxes[r] if boxes else None) for r in range(world)]
     for sh in shards:
         sh.load(rows, c, max_pivots=cap)
 
     def gather_all():
         torch.cuda.synchronize()                       # emulation only: every rank's send is complete
-        for sh in shards:
-            for g, other in enumerate(shards):
-                sh.gathered[g].copy_(other.send)
+        if boxes:
+            for sh in shards:                          # each rank pushes into every box, then everyone proceeds
+                sh.phase_exchange()
+        else:
+            for sh in shards:
+                for g, other in enumerate(shards):
+                    sh.gathered[g].copy_(other.send)
         torch.cuda.synchronize()
 
     def lockstep(fn_local, fn_global):
@@ -382,7 +393,8 @@ def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookah
 
         def first_global(sh):
             cur, si = sh.npiv_enqueued & 1, sh.si
-            sh.ops.select(sh.gathered, sh.world, sh.b[cur], sh.n, sh.rule, sh.states[si], sh.colbufs[si])
+            gathered, flags, seq = sh._gathered_and_flags()
+            sh.ops.select(gathered, sh.world, sh.b[cur], sh.n, sh.rule, sh.states[si], sh.colbufs[si], flags, seq)
             sh.priced = True
         lockstep(first_local, first_global)
     for _ in range(cap + 3):                           # a few steps past the ending: terminal states propagate
@@ -401,6 +413,9 @@ def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookah
     ob[:n] = o.table[: n * (m + 1)].reshape(n, m + 1)[:, :m]
     ob[n] = o.table[n * (m + 1):]
     assert np.array_equal(bits(body), bits(ob))
+    if boxes:
+        for bx in boxes:
+            bx.close()
 
 
 # --------------------------------------------------------------------------- BASELINE configs

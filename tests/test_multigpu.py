@@ -1,0 +1,91 @@
+"""Real multi-GPU test of the column-sharded flow (needs >= 2 CUDA devices; skipped otherwise):
+one process per GPU, the C-side look-ahead loop with NVLink peer mailboxes (PeerShardedTableau) and
+the NCCL all-gather flow (ShardedTableau), each against the single-process oracle, bit for bit.
+Run with:  gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu -q
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, m, seed, cap, mode, out):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from simplex_method_solver_b200 import parallel as P
+        from simplex_method_solver_b200 import workloads as W
+        rows, c = W.dense_lp(n, m, seed)
+        if mode == "p2p":
+            sh = P.PeerShardedTableau(n, m, rank, world, dev, trace_capacity=cap + 8)
+        else:
+            sh = P.ShardedTableau(n, m, rank, world, dev, trace_capacity=cap + 8, lookahead=(mode == "nccl-ahead"))
+        sh.load(rows, c, max_pivots=cap)
+        status, npiv = sh.solve(cap, check_every=16)
+        st = sh.sync()
+        body = sh.local_body().cpu().numpy().copy() if mode != "p2p" else \
+            sh.A[sh._cur, :, : sh.m_loc].cpu().numpy().copy()
+        b = (sh.b[sh._cur, :n] if mode == "p2p" else sh.b_current()).cpu().numpy().copy()
+        out.put((rank, {"status": int(st.status), "npiv": int(st.npiv), "col0": sh.col0, "body": body, "b": b,
+                        "trace": sh.trace[: int(st.npiv)].cpu().numpy().copy(),
+                        "rowlab": sh.rowlab.cpu().numpy().copy(), "collab": sh.collab[:n].cpu().numpy().copy()}))
+        dist.barrier()
+        if mode == "p2p":
+            sh.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["p2p", "nccl", "nccl-ahead"])
+@pytest.mark.parametrize("n,m,cap", [(300, 2600, 150), (64, 1024, 400)])
+def test_sharded_flow_on_real_gpus(mode, n, m, cap):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import oracle
+    from simplex_method_solver_b200 import workloads as W
+    rows, c = W.dense_lp(n, m, 7)
+    o = oracle.solve(rows, c, max_pivots=cap)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, m, 7, cap, mode, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    body = np.zeros((n + 1, m))
+    for r in range(world):
+        g = got[r]
+        assert (g["status"], g["npiv"]) == (o.status, o.npiv), (mode, r, g["status"], g["npiv"], o.status, o.npiv)
+        assert g["trace"].tolist() == o.trace.tolist()
+        assert g["rowlab"].tolist() == o.rowlab.tolist() and g["collab"].tolist() == o.collab.tolist()
+        body[:, g["col0"]: g["col0"] + g["body"].shape[1]] = g["body"]
+        assert np.array_equal(g["b"].view(np.uint64), o.table[: n * (m + 1)].reshape(n, m + 1)[:, m].copy().view(np.uint64))
+    ob = np.zeros((n + 1, m))
+    ob[:n] = o.table[: n * (m + 1)].reshape(n, m + 1)[:, :m]
+    ob[n] = o.table[n * (m + 1):]
+    assert np.array_equal(body.view(np.uint64), ob.view(np.uint64))

@@ -90,7 +90,7 @@ def _run_world(world, n, m, seed, cap, kind, lookahead):
              for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(out.get(timeout=120) for _ in range(world))
+    got = dict(out.get(timeout=60) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
