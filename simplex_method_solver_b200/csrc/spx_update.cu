@@ -10,13 +10,13 @@
 //
 // Two kernels, same arithmetic, same results:
 //
-//  update_tiled_kernel      one CTA per tile of TR rows x 512 columns; a thread
+//  update_tiled_kernel      one CTA per tile of TR (default 8) rows x 512 columns; a thread
 //      owns two adjacent columns (one 128-bit access per row) and walks down the
 //      rows: fully coalesced 512-byte line groups, the thread's two pivot-row
 //      values in registers, the column multiplier a shared-memory broadcast.  The
 //      pivot-row slice and the pivot-column slice are staged with two
-//      cp.async.bulk (TMA, SASS UBLKCP) copies on one mbarrier.  Used for tableaus
-//      that fit L2 (latency-bound: many small CTAs, 8 rows in flight per thread).
+//      cp.async.bulk (TMA, SASS UBLKCP) copies on one mbarrier.  The default at every
+//      size: 8 rows in flight per thread, 4 CTAs per SM (64 registers), 6.8 TB/s at cfg4.
 //
 //  update_pipelined_kernel  persistent, warp-specialised, one CTA per SM: a
 //      producer lane streams tiles of 8 rows x 512 columns (32 KB) into a 6-stage
@@ -24,8 +24,8 @@
 //      the pivot column and, when the column tile changes, of the pivot row);
 //      8 consumer warps read the stage with conflict-free 128-bit LDS, release it,
 //      compute and store straight to HBM with 128-bit streaming stores.  Up to
-//      ~190 KB of reads in flight per SM independent of register count: the HBM
-//      streaming path for tableaus larger than L2.
+//      ~190 KB of reads in flight per SM independent of register count.  Measured
+//      slower than the tiled kernel (5.5 vs 6.8 TB/s); selectable with spx_set_option.
 //
 // Fused into the same pass: the b ('-b') column update, the label swap
 // (:152), the pivot trace, and the pricing of the NEXT pivot (first negative
@@ -431,18 +431,19 @@ int64_t colbuf_doubles(int n) {
     return ((int64_t)n + 1 + UPD_TR_MAX - 1) / UPD_TR_MAX * UPD_TR_MAX + UPD_TR_MAX;
 }
 
-// rows per tile: 64 for big tableaus; smaller (multiple of 8) when that is what it
-// takes to put at least ~4 CTAs on every SM of the device
+int64_t g_opt[8] = {0, 0, 4, 0, 0, 0, 0, 0};
+
+// Rows per tile.  Measured on B200 (tools/upd_lab.py, profiles/r1c_update_variants.md): the smallest
+// tile — 8 rows = exactly one 8-deep load batch per thread, 4 CTAs (64 registers) per SM — is the
+// fastest at every size: 16384 x 32768 streams at 6.79 TB/s (64 rows: 6.60), and the 4096-column
+// shard of the 8-GPU split at 5.9 TB/s (64 rows: 4.8, wave quantisation: 2056 CTAs on 444 slots).
 static int pick_tr(int n, int m_loc) {
-    const int64_t ctiles = ((int64_t)m_loc + UPD_TC - 1) / UPD_TC;
-    const int64_t want = 4LL * sm_count();
-    int tr = UPD_TR_MAX;
-    while (tr > 8 && ctiles * (((int64_t)n + 1 + tr - 1) / tr) < want) tr -= 8;
-    return tr;
+    (void)n; (void)m_loc;
+    if (g_opt[SPX_OPT_TILED_ROWS] > 0) return (int)g_opt[SPX_OPT_TILED_ROWS];
+    return 8;
 }
 
 // process-wide tuning knobs (spx_set_option); every setting computes the same bits
-int64_t g_opt[8] = {0, 0, 3, 0, 0, 0, 0, 0};
 
 int64_t get_option(int key) { return (key >= 0 && key < 8) ? g_opt[key] : -1; }
 int set_option(int key, int64_t value) {
@@ -451,6 +452,7 @@ int set_option(int key, int64_t value) {
     case SPX_OPT_TILED_MIN_BLOCKS: if (value < 1 || value > 4) return -1; break;
     case SPX_OPT_PIPE_ORDER:       if (value < 0 || value > 1) return -1; break;
     case SPX_OPT_PIPE_GRID:        if (value < 0 || value > 4096) return -1; break;
+    case SPX_OPT_TILED_ROWS:       if (value < 0 || value > UPD_TR_MAX || value % 8) return -1; break;
     default: return -1;
     }
     g_opt[key] = value;
@@ -491,8 +493,8 @@ cudaError_t update(const double *Ain, double *Aout, const double *bin, double *b
     switch ((int)g_opt[SPX_OPT_TILED_MIN_BLOCKS]) {
     case 1: SPX_LAUNCH_TILED(1); break;
     case 2: SPX_LAUNCH_TILED(2); break;
-    case 4: SPX_LAUNCH_TILED(4); break;
-    default: SPX_LAUNCH_TILED(3); break;
+    case 3: SPX_LAUNCH_TILED(3); break;
+    default: SPX_LAUNCH_TILED(4); break;
     }
 #undef SPX_LAUNCH_TILED
     spx_host::count_launch();

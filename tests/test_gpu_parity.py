@@ -307,7 +307,8 @@ def test_hoisted_reciprocal_division_equals_div_rn(spx):
 
 
 @pytest.mark.parametrize("opts", [{1: 1, 2: 2}, {1: 1, 2: 3}, {1: 1, 2: 4}, {1: 2, 3: 0}, {1: 2, 3: 1},
-                                  {1: 2, 3: 0, 4: 7}, {1: 2, 3: 1, 4: 5}])
+                                  {1: 2, 3: 0, 4: 7}, {1: 2, 3: 1, 4: 5}, {1: 1, 2: 3, 5: 64}, {1: 1, 2: 4, 5: 24},
+                                  {1: 1, 2: 2, 5: 16}])
 def test_every_update_kernel_variant_is_bit_exact(spx, opts):
     """Tiled (every register budget) and TMA-pipelined (both tile orders, odd grids) update kernels
     against the oracle on ragged shapes, including tiles with the pivot row/column and the f row."""
@@ -334,7 +335,7 @@ def test_every_update_kernel_variant_is_bit_exact(spx, opts):
                 T = oracle.update(T, n, m, r, cc)
                 assert np.array_equal(bits(dev.export_flat(npiv + 1)), bits(T)), (opts, n, m, npiv)
     finally:
-        for k, v in {1: 0, 2: 3, 3: 0, 4: 0}.items():
+        for k, v in {1: 0, 2: 4, 3: 0, 4: 0, 5: 0}.items():
             L.spx_set_option(k, v)
 
 

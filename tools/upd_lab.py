@@ -37,11 +37,16 @@ def main():
     del rows
     cells = n * (m + 1) + m
     variants = [
-        ("tiled minb=2", {1: 1, 2: 2}),
-        ("tiled minb=3", {1: 1, 2: 3}),
-        ("tiled minb=4", {1: 1, 2: 4}),
+        ("tiled minb=2", {1: 1, 2: 2, 5: 0}),
+        ("tiled minb=3", {1: 1, 2: 3, 5: 0}),
+        ("tiled minb=4", {1: 1, 2: 4, 5: 0}),
         ("pipe order=0 grid=sm", {1: 2, 3: 0, 4: 0}),
         ("pipe order=1 grid=sm", {1: 2, 3: 1, 4: 0}),
+        ("tiled minb=3 tr=32", {1: 1, 2: 3, 5: 32}),
+        ("tiled minb=3 tr=16", {1: 1, 2: 3, 5: 16}),
+        ("tiled minb=3 tr=8", {1: 1, 2: 3, 5: 8}),
+        ("tiled minb=4 tr=16", {1: 1, 2: 4, 5: 16}),
+        ("tiled minb=4 tr=8", {1: 1, 2: 4, 5: 8}),
     ]
     if args.variants:
         keep = set(args.variants.split(","))
