@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define SPX_ABI_VERSION 2
+#define SPX_ABI_VERSION 3
 
 /* status codes == the outcomes of pick_element(), simplex.py:70-141 */
 #define SPX_PIVOT       1   /* (True, r, c, e)                                   :91,:141 */
@@ -153,19 +153,24 @@ int spx_update(const double *d_Ain, double *d_Aout, const double *d_bin, double 
  * the current table — SPX_PIVOT, or its terminal status).  d_trace is [max_pivots][2] int32 or NULL.
  * On return *h_status / *h_npiv mirror d_state.
  *
- * d_work == NULL: classic order pick k, update k, pick k+1, ... on `stream`.
- * d_work != NULL (128-byte aligned, >= spx_solve_workspace_bytes(n)): LOOK-AHEAD.  While the
+ * mode SPX_LOOP_CLASSIC: pick k, update k, pick k+1, ... on `stream`.
+ * mode SPX_LOOP_LOOKAHEAD (d_work 128-byte aligned, >= spx_solve_workspace_bytes(n)): while the
  * streaming update of pivot k runs on `stream`, a high-priority side stream owned by the
  * library prices pivot k+1 from the same (old) table — the next b column, the next f /
  * phase-1 row and the next entering column are O(n+m) cells computed with the update's own
  * arithmetic — so the update kernels run back to back and pricing is off the critical path.
  * Pivot sequence and every cell are identical in both modes. */
+#define SPX_LOOP_AUTO      0  /* resident if the tableau fits L2, look-ahead if >= 256 MB and a workspace is given, else classic */
+#define SPX_LOOP_CLASSIC   1
+#define SPX_LOOP_LOOKAHEAD 2
+#define SPX_LOOP_RESIDENT  3  /* ONE persistent cooperative kernel runs the whole loop (n <= 4095, both bodies in L2):
+                               * every CTA prices the pivot redundantly, one grid barrier per pivot (csrc/spx_resident.cu) */
 int64_t spx_solve_workspace_bytes(int32_t n);
 int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1,
               int32_t n, int32_t m, int64_t ld, int32_t rule,
               spx_state *d_state, double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab,
               int32_t *d_trace, int32_t chunk, int64_t stop_after,
-              void *d_work, int64_t work_bytes,
+              int32_t mode, void *d_work, int64_t work_bytes,
               int32_t *h_status, int64_t *h_npiv, void *stream);
 
 /* ---- find_optimum() / f(), simplex.py:48-68, generalised to m variables --- */

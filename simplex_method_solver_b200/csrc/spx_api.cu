@@ -28,6 +28,9 @@ cudaError_t ahead_select(const double *, int, const double *, int, const spx_sta
                          double *, const unsigned long long *, unsigned long long, cudaStream_t);
 cudaError_t extract(const double *, int, int, const int32_t *, const double *, double *, double *,
                     cudaStream_t);
+bool resident_fits(int, int, int64_t);
+cudaError_t resident_loop(double *, double *, double *, double *, int, int, int64_t, int, int64_t, spx_state *,
+                          double *, int32_t *, int32_t *, int32_t *, cudaStream_t);
 int64_t get_option(int);
 int     set_option(int, int64_t);
 cudaError_t selftest_division(const double *, const double *, int64_t, int64_t, unsigned long long *,
@@ -290,14 +293,24 @@ int64_t spx_solve_workspace_bytes(int32_t n) { return workspace_bytes(n); }
 
 int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n, int32_t m, int64_t ld,
               int32_t rule, spx_state *d_state, double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab,
-              int32_t *d_trace, int32_t chunk, int64_t stop_after, void *d_work, int64_t work_bytes,
-              int32_t *h_status, int64_t *h_npiv, void *stream) {
+              int32_t *d_trace, int32_t chunk, int64_t stop_after, int32_t mode, void *d_work,
+              int64_t work_bytes, int32_t *h_status, int64_t *h_npiv, void *stream) {
     if (validate_split("spx_solve", d_A0, d_b0, n, m, ld)) return -2;
     if (validate_split("spx_solve", d_A1, d_b1, n, m, ld)) return -2;
     SPX_REQUIRE(d_state && d_colbuf && d_rowlab && d_collab, "spx_solve: null state/colbuf/labels");
     SPX_REQUIRE(chunk >= 1, "spx_solve: chunk must be >= 1");
     SPX_REQUIRE(rule == SPX_RULE_REFERENCE || rule == SPX_RULE_DANTZIG, "spx_solve: unknown rule %d", rule);
-    const bool ahead = (d_work != nullptr);
+    SPX_REQUIRE(mode >= SPX_LOOP_AUTO && mode <= SPX_LOOP_RESIDENT, "spx_solve: unknown mode %d", mode);
+    if (mode == SPX_LOOP_AUTO) {
+        // L2-resident tableaus: one persistent kernel; big ones: look-ahead streaming; else classic
+        if (spx_launch::resident_fits(n, m, ld)) mode = SPX_LOOP_RESIDENT;
+        else if (d_work != nullptr && (int64_t)(n + 1) * ld * 8 >= (256LL << 20)) mode = SPX_LOOP_LOOKAHEAD;
+        else mode = SPX_LOOP_CLASSIC;
+    }
+    SPX_REQUIRE(mode != SPX_LOOP_RESIDENT || spx_launch::resident_fits(n, m, ld),
+                "spx_solve: the tableau does not fit the L2-resident loop (n <= 4095, 2 bodies <= 96 MB, cooperative launch)");
+    SPX_REQUIRE(mode != SPX_LOOP_LOOKAHEAD || d_work != nullptr, "spx_solve: look-ahead needs a workspace");
+    const bool ahead = (mode == SPX_LOOP_LOOKAHEAD);
     SPX_REQUIRE(!ahead || (work_bytes >= workspace_bytes(n) && ((uintptr_t)d_work & 127) == 0),
                 "spx_solve: workspace must be 128-byte aligned and >= spx_solve_workspace_bytes(n) = %lld bytes",
                 (long long)workspace_bytes(n));
@@ -325,6 +338,18 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
         if (stop_after > 0 && stop_after - done < k) k = stop_after - done;
         if (k <= 0) break;
         const int64_t base = hs.npiv;
+        if (mode == SPX_LOOP_RESIDENT) {
+            // one persistent cooperative launch applies up to k pivots (or all of them)
+            if (stop_after <= 0) k = 1LL << 40;
+            else k = stop_after - done;
+            if (check(spx_launch::resident_loop(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, k, d_state, d_colbuf,
+                                                d_rowlab, d_collab, d_trace, s), "resident launch")) return -1;
+            if (check(cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, s), "read state")) return -1;
+            if (check(cudaStreamSynchronize(s), "resident loop")) return -1;
+            done += hs.npiv - base;
+            if (hs.status == SPX_PIVOT && hs.npiv == base) break;     // defensive: no progress
+            continue;
+        }
         if (!ahead) {
             // classic: pick k, update k, pick k+1, ... on one stream
             for (int64_t q = 0; q < k; ++q) {

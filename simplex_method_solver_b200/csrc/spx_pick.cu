@@ -10,79 +10,15 @@
 // The same building blocks serve the column-sharded flow: `candidate` is the
 // local half of K1 (+ column gather into the all-gather message), `select` is
 // the global half of K1 (min key over ranks) + K2 on the winning column.
-#include "spx_common.cuh"
+#include "spx_block.cuh"
 
 namespace {
 
 using namespace spx;
 
 constexpr int PICK_THREADS = 1024;
-constexpr int PICK_WARPS   = PICK_THREADS / 32;
 constexpr int MSG_HEADER   = 4;      // doubles: [key_hi, key_lo, r_phase1, reserved]
 constexpr int GATHER_BATCH = 8;      // independent loads in flight per thread in the O(n) loops
-
-struct Scratch {
-    int                red_i[PICK_WARPS];
-    unsigned long long red_k[PICK_WARPS];
-    Ratio              red_q[PICK_WARPS];
-    int                out_i;
-    unsigned long long out_k;
-    Ratio              out_q;
-};
-
-__device__ __forceinline__ int block_min_int(int v, Scratch &s) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    v = warp_min_int(v);
-    if (lane == 0) s.red_i[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        int w = warp_min_int(lane < (int)(blockDim.x >> 5) ? s.red_i[lane] : SPX_NONE);
-        if (lane == 0) s.out_i = w;
-    }
-    __syncthreads();
-    const int out = s.out_i;
-    __syncthreads();
-    return out;
-}
-
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) {
-        unsigned long long o = __shfl_xor_sync(0xffffffffu, v, sft);
-        v = o < v ? o : v;
-    }
-    return v;
-}
-
-__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, Scratch &s) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    v = warp_min_u64(v);
-    if (lane == 0) s.red_k[warp] = v;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long w = warp_min_u64(lane < (int)(blockDim.x >> 5) ? s.red_k[lane] : ~0ull);
-        if (lane == 0) s.out_k = w;
-    }
-    __syncthreads();
-    const unsigned long long out = s.out_k;
-    __syncthreads();
-    return out;
-}
-
-__device__ __forceinline__ Ratio block_ratio_reduce(Ratio q, Scratch &s) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    q = warp_ratio_reduce(q);
-    if (lane == 0) s.red_q[warp] = q;
-    __syncthreads();
-    if (warp == 0) {
-        Ratio w = warp_ratio_reduce(lane < (int)(blockDim.x >> 5) ? s.red_q[lane] : ratio_identity());
-        if (lane == 0) s.out_q = w;
-    }
-    __syncthreads();
-    const Ratio out = s.out_q;
-    __syncthreads();
-    return out;
-}
 
 // ---- peer mailboxes (column-sharded flow over NVLink peer memory) ------------------
 // Every rank's candidate message is stored by its owner straight into each peer's mailbox
@@ -109,44 +45,6 @@ __device__ bool wait_flags(const unsigned long long *flags, int nranks, unsigned
         }
     }
     return __syncthreads_or(ok ? 0 : 1) == 0;
-}
-
-struct IsNeg { __device__ bool operator()(double v) const { return v < 0.0; } };   // :74, :96
-struct IsPos { __device__ bool operator()(double v) const { return v > 0.0; } };   // :83
-
-// first j in [0, len) with pred(x[j]); chunked so the usual early hit costs one pass
-template <class Pred>
-__device__ int block_first_index(const double *__restrict__ x, int len, Pred pred, Scratch &s) {
-    const int nt = (int)blockDim.x;
-    for (int base = 0; base < len; base += nt * 4) {
-        int loc = SPX_NONE;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = base + u * nt + (int)threadIdx.x;
-            if (j < len && pred(x[j])) loc = min(loc, j);
-        }
-        loc = block_min_int(loc, s);
-        if (loc != SPX_NONE) return loc;
-    }
-    return SPX_NONE;
-}
-
-// same search over values produced on the fly: val(j) is the cell j of a row that does not
-// exist in memory yet (the look-ahead kernels price the NEXT table from the current one)
-template <class Val, class Pred>
-__device__ int block_first_index_fn(int len, Val val, Pred pred, Scratch &s) {
-    const int nt = (int)blockDim.x;
-    for (int base = 0; base < len; base += nt * 4) {
-        int loc = SPX_NONE;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = base + u * nt + (int)threadIdx.x;
-            if (j < len && pred(val(j))) loc = min(loc, j);
-        }
-        loc = block_min_int(loc, s);
-        if (loc != SPX_NONE) return loc;
-    }
-    return SPX_NONE;
 }
 
 // K1 on the columns [0, m_loc) this CTA can see.

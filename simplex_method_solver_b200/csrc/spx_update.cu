@@ -42,26 +42,6 @@ constexpr int UPD_TC      = 2 * UPD_THREADS;   // columns per tile
 constexpr int UPD_TR_MAX  = 64;                // rows per tile (upper bound; multiple of 8)
 constexpr int UPD_UNROLL  = 8;
 
-// One output pair of row i (global row index), generic: handles the pivot row (:155-156),
-// the pivot column (:159-160), the pivot cell (:163) and ordinary cells (:166-175).
-// jc = 0/1 when this thread's .x/.y is the pivot column, -1 otherwise.
-__device__ __forceinline__ double2 generic_pair(double2 t, int i, int r, int jc, double2 rj, double ci,
-                                                const PivotDiv &d) {
-    double2 o;
-    if (i == r) {
-        o.x = pivot_div(-t.x, d);
-        o.y = pivot_div(-t.y, d);
-        if (jc == 0) o.x = pivot_cell_update(d.p);
-        if (jc == 1) o.y = pivot_cell_update(d.p);
-    } else {
-        o.x = cell_update(t.x, d, rj.x, ci);
-        o.y = cell_update(t.y, d, rj.y, ci);
-        if (jc == 0) o.x = pivot_div(ci, d);
-        if (jc == 1) o.y = pivot_div(ci, d);
-    }
-    return o;
-}
-
 // the '-b' column (replicated when column-sharded) for rows [row_begin, row_end) + hint
 __device__ __forceinline__ void update_b_rows(const double *__restrict__ bin, double *__restrict__ bout,
                                               const double *__restrict__ colbuf, int n, int r,

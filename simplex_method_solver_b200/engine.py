@@ -79,13 +79,6 @@ class DeviceTableau:
         self.max_pivots = int(max_pivots)
         self._keepalive = None
 
-    # look-ahead pays when one update is long enough to hide the side-stream pricing and the
-    # extra enqueues per pivot; small (L2-resident) tableaus keep the classic two-launch loop
-    LOOKAHEAD_MIN_BYTES = 256 << 20
-
-    def lookahead_default(self) -> bool:
-        return (self.n + 1) * self.ld * 8 >= self.LOOKAHEAD_MIN_BYTES
-
     # -- plumbing ---------------------------------------------------------------
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -147,18 +140,19 @@ class DeviceTableau:
               lookahead=None):
         """Run the pivot loop on the device until a terminal status / cap / stop_after.
 
-        lookahead: price pivot k+1 on a side stream while update k streams (None: by size).
+        lookahead selects the loop (all give identical results): None/"auto" — by size: the
+        persistent L2-resident kernel for small tableaus, look-ahead streaming for big ones;
+        False/"classic" — pick k, update k, ...; True/"lookahead" — price pivot k+1 on a side
+        stream while update k streams; "resident" — the persistent cooperative kernel.
         """
         st, npiv = ctypes.c_int32(0), ctypes.c_int64(0)
-        if lookahead is None:
-            lookahead = self.lookahead_default()
-        work, wbytes = (self.work.data_ptr(), self.work.numel() * 8) if lookahead else (None, 0)
+        mode = N.LOOP_MODES[lookahead]
         with torch.cuda.device(self.device):
             N.call("spx_solve", self.A[0].data_ptr(), self.A[1].data_ptr(), self.b[0].data_ptr(),
                    self.b[1].data_ptr(), self.n, self.m, self.ld, rule, self.state.data_ptr(),
                    self.colbuf.data_ptr(), self.rowlab.data_ptr(), self.collab.data_ptr(),
-                   N.ptr(self.trace), int(chunk), int(stop_after), work, wbytes, ctypes.byref(st),
-                   ctypes.byref(npiv), self._stream())
+                   N.ptr(self.trace), int(chunk), int(stop_after), mode, self.work.data_ptr(),
+                   self.work.numel() * 8, ctypes.byref(st), ctypes.byref(npiv), self._stream())
         return st.value, npiv.value
 
     # -- results ----------------------------------------------------------------------

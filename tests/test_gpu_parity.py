@@ -71,8 +71,35 @@ def test_cfg1_snapshot_digest(spx, ref_cases):
     assert res[-1].optimum == -65.2785688917863
 
 
+def test_gui_adapter_compute_solution(spx, ref_cases):
+    """N1: the headless compute_solution call site returns the reference's Info list and table views."""
+    from simplex_method_solver_b200 import gui_adapter as G
+    case = next(c for c in ref_cases if c["name"] == "ref_example_cfg1_205")
+    sol = G.compute_solution(lines=W.CFG1_ROWS, grad=W.CFG1_C + [0])
+    assert not sol.failed and len(sol.tables) == len(case["get_solution"]) == 5
+    view = G.table_view(sol.tables[0])
+    assert view["pivot"] == (2, 0) and view["optimum"] == 0 and view["f"] == [-1.0, -1.0]
+    assert view["body"][0] == [-39.7, -96.0, 4060.8]
+    last = G.table_view(sol.tables[-1])
+    assert last["pivot"] is None and last["optimum"] == -65.28
+    assert last["point"] == (39.18192919380969, 26.096639697976617)
+    bad = G.compute_solution(lines=[[1.0, 1.0, -2.0], [-1.0, -1.0, 1.0]], grad=[1.0, 1.0, 0])
+    assert bad.failed and str(bad.tables[-1]) == "incorrect system"
+
+
+def test_problem_files_feed_the_batched_solver(spx):
+    """N3: problems in the GUI's text format -> one batched solve == per-problem oracle solves."""
+    from simplex_method_solver_b200 import problem_io as PIO
+    T, C = W.gui_batch(64, seed=9)
+    probs = [PIO.loads(PIO.dumps(T[k].tolist(), C[k].tolist() + [0], 10)) for k in range(64)]
+    tabs, n, m = PIO.batch_tables(probs)
+    res = spx.batched.solve_batched(tabs, n, m, max_pivots=64)
+    orc = oracle.solve_batched(tabs, n, m, max_pivots=64)
+    assert res.trace.tobytes() == orc.trace.tobytes() and res.x.tobytes() == orc.x.tobytes()
+
+
 # --------------------------------------------------------------------------- all golden cases
-@pytest.mark.parametrize("lookahead,chunk", [(False, 7), (True, 7), (True, 4), (True, 1)])
+@pytest.mark.parametrize("lookahead,chunk", [(False, 7), (True, 7), (True, 4), (True, 1), ("resident", 7), (None, 5)])
 def test_all_reference_cases_streaming_solver(spx, ref_cases, lookahead, chunk):
     """solve(): device-side loop, classic (pick k, update k, ...) and look-ahead (pivot k+1 priced
     from table k on a side stream while update k runs); trace, ending, labels, final table bits."""
@@ -148,18 +175,19 @@ def test_step_api_matches_oracle(spx):
                 break
 
 
-def test_lookahead_state_feeds_the_step_api_and_resumes(spx):
-    """A look-ahead solve stopped by the cap leaves a state the step API and a resumed solve continue from."""
+@pytest.mark.parametrize("mode", [True, "resident"])
+def test_lookahead_state_feeds_the_step_api_and_resumes(spx, mode):
+    """A look-ahead / resident solve stopped by the cap leaves a state the step API and a resumed solve continue from."""
     rows, c = W.dense_lp(40, 70, 9)
     ref = oracle.solve(rows, c, max_pivots=10000)
     assert ref.status == oracle.OPTIMAL and ref.npiv > 25
     sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
-    sol = sm.solve(max_pivots=11, chunk=4, lookahead=True)
+    sol = sm.solve(max_pivots=11, chunk=4, lookahead=mode)
     assert sol.status == spx.N.CAP and sol.trace.tolist() == ref.trace[:11].tolist()
     ok, r, cc, e = sm.pick_element()
     assert ok and [r, cc] == ref.trace[11].tolist()
     sm.recalculate_matrix()
-    sol = sm.solve(max_pivots=10000, chunk=5, lookahead=True)
+    sol = sm.solve(max_pivots=10000, chunk=5, lookahead=mode)
     assert sol.status == spx.N.OPTIMAL and sol.npiv == ref.npiv
     # pivot 11 went through the step API after the traced capacity of the first solve: not traced
     assert sol.trace[:11].tolist() == ref.trace[:11].tolist()
@@ -168,7 +196,7 @@ def test_lookahead_state_feeds_the_step_api_and_resumes(spx):
     assert sol.x.tobytes() == ref.x.tobytes()
 
 
-@pytest.mark.parametrize("lookahead", [False, True])
+@pytest.mark.parametrize("lookahead", [False, True, "resident"])
 def test_dantzig_rule_modes_agree(spx, lookahead):
     """rule='dantzig' (extension, not reference behaviour): classic and look-ahead give one trace."""
     rows, c = W.dense_lp(30, 50, 4)
@@ -228,6 +256,37 @@ def test_pick_update_bit_exact_ragged_shapes(spx, n, m):
         got = dev.export_flat(npiv)
         assert np.array_equal(bits(got), bits(T)), f"step {step}"
         assert dev.read_state().npiv == npiv
+
+
+@pytest.mark.parametrize("n,m", [(1, 2), (3, 1), (7, 15), (9, 17), (64, 512), (65, 513), (130, 1030), (257, 100), (40, 2049)])
+def test_resident_loop_bit_exact_ragged_shapes(spx, n, m):
+    """The persistent L2-resident loop in steps of 1..3 pivots vs the oracle, whole table each time."""
+    rng = np.random.default_rng(n * 31 + m)
+    rows, c = W.dense_lp(n, m, seed=n + 2 * m)
+    rows[rng.random(rows.shape) < 0.05] = 0.0
+    dev = spx.engine.DeviceTableau(n, m, trace_capacity=64)
+    dev.load(rows, c, max_pivots=64)
+    T = flat_of(rows, c)
+    npiv = 0
+    for k in (1, 2, 3, 1, 3):
+        want = []
+        for _ in range(k):
+            st, r, cc, e = oracle.pick(T, n, m)
+            if st != oracle.PIVOT:
+                break
+            want.append([r, cc])
+            T = oracle.update(T, n, m, r, cc)
+        status, got = dev.solve(stop_after=k, lookahead="resident")
+        assert got == npiv + len(want)
+        assert dev.trace[npiv:got].cpu().numpy().tolist() == want
+        npiv = got
+        assert np.array_equal(bits(dev.export_flat(npiv)), bits(T)), (n, m, npiv)
+        st, r, cc, e = oracle.pick(T, n, m)
+        assert status == st
+        if st != oracle.PIVOT:
+            break
+        s_ = dev.read_state()
+        assert (s_.r, s_.c, s_.p) == (r, cc, e)          # priced, not yet applied
 
 
 def test_ratio_scan_special_values(spx):
@@ -420,7 +479,7 @@ def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookah
 
 
 # --------------------------------------------------------------------------- BASELINE configs
-@pytest.mark.parametrize("lookahead", [False, True])
+@pytest.mark.parametrize("lookahead", [False, True, "resident"])
 def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests, lookahead):
     g = cfg_digests["cfg2"]
     rows, c = W.dense_lp(1000, 2000, 0)
@@ -478,7 +537,7 @@ def test_cfg5_klee_minty(spx, cfg_digests, n):
     assert res.x[0, n - 1] == float(5 ** n) and (res.x[0, : n - 1] == 0).all()
 
 
-@pytest.mark.parametrize("lookahead", [False, True])
+@pytest.mark.parametrize("lookahead", [False, True, "resident"])
 def test_cfg5_klee_minty10_streaming_equals_batched(spx, cfg_digests, lookahead):
     rows, c = W.klee_minty(10)
     sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
