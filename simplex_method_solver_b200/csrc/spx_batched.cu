@@ -65,9 +65,61 @@ __device__ __forceinline__ int warp_ratio_decide(const Ratio &q, bool my_elig_na
     return (zero != SPX_NONE) ? zero : -1;                                 // first zero ratio, else min_val > 0
 }
 
-__global__ void __launch_bounds__(256, 4)
+// K1 + K2 by ONE warp on the shared-memory table `cur`: returns SPX_PIVOT with (r, c) or the
+// terminal status.  All 32 lanes take the same branches (ballots / redux only).
+__device__ __forceinline__ int warp_pick(const double *cur, int n, int m, int rule, int lane, int &r, int &c) {
+    const int w1 = m + 1, fo = n * w1;
+    // ---- K1: phase-1 row (:72-76), its first positive cell (:81-85) ...
+    const int r1 = warp_first_index(n, lane, [&](int i) { return cur[i * w1 + m] < 0.0; });
+    if (r1 != SPX_NONE) {
+        c = warp_first_index(m, lane, [&](int j) { return cur[r1 * w1 + j] > 0.0; });
+        if (c == SPX_NONE) return SPX_INCORRECT;                                  // :88-89
+        r = r1;                                                                   // :91
+        return SPX_PIVOT;
+    }
+    // ---- ... or the entering column from the f row (:94-98)
+    if (rule == SPX_RULE_REFERENCE) {
+        c = warp_first_index(m, lane, [&](int j) { return cur[fo + j] < 0.0; });
+    } else {   // Dantzig: most negative, lowest index on ties
+        unsigned long long best = ~0ull;
+        for (int j = lane; j < m; j += 32) {
+            const double v = cur[fo + j];
+            if (v < 0.0) { const unsigned long long k = orderable(v); best = k < best ? k : best; }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, s);
+            best = o < best ? o : best;
+        }
+        c = (best == ~0ull) ? SPX_NONE
+            : warp_first_index(m, lane, [&](int j) {
+                  const double v = cur[fo + j];
+                  return v < 0.0 && orderable(v) == best; });
+    }
+    if (c == SPX_NONE) return SPX_OPTIMAL;                                        // :101-103
+    // ---- K2: the ratio scan (:107-136): lane-local fold, then ballots / redux across lanes
+    Ratio q = ratio_identity();
+    bool my_elig_nan = false;                    // is the ratio of MY first eligible row NaN?
+    for (int i = lane; i < n; i += 32) {
+        const double a_ic = cur[i * w1 + c], b_i = cur[i * w1 + m];
+        const bool first = (q.elig_row == SPX_NONE);
+        const bool is_nan = ratio_accumulate(q, i, a_ic, b_i);
+        if (first && q.elig_row != SPX_NONE) my_elig_nan = is_nan;
+    }
+    r = warp_ratio_decide(q, my_elig_nan, lane);
+    return (r < 0) ? SPX_NOCONV : SPX_PIVOT;                                      // :138-139
+}
+
+// CTA == false: one warp per LP, warps_per_cta LPs per CTA, __syncwarp between the phases
+//               (cfg1: 14 cells, cfg3: 26 cells — one cell per lane).
+// CTA == true : one CTA per LP for tables of hundreds of cells (Klee-Minty n=20: 440 cells, 2^20-1
+//               strictly sequential pivots): warp 0 prices the pivot, every warp updates its share
+//               of the cells, two block barriers per pivot.
+template <bool CTA>
+__global__ void __launch_bounds__(256, CTA ? 1 : 4)
 batched_kernel(BatchedArgs a, int warps_per_cta, int warp_doubles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_ctl[4];                               // CTA mode: {status, r, c} of warp 0's pick
     const int n = a.n, m = a.m, w1 = m + 1;
     const int cells = n * w1 + m;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -82,11 +134,14 @@ batched_kernel(BatchedArgs a, int warps_per_cta, int warp_doubles) {
     }
     __syncthreads();
 
-    const int64_t lp = (int64_t)blockIdx.x * warps_per_cta + warp;
-    if (warp >= warps_per_cta || lp >= a.B) return;
+    const int64_t lp = CTA ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * warps_per_cta + warp;
+    if (!CTA && (warp >= warps_per_cta || lp >= a.B)) return;
+    const int tl = CTA ? (int)threadIdx.x : lane;          // thread index within the LP's group
+    const int nl = CTA ? (int)blockDim.x : 32;             // threads of the group
+    auto group_sync = [&]() { if (CTA) __syncthreads(); else __syncwarp(); };
 
     const size_t lut_bytes = ((size_t)cells * 4 + 15) / 16 * 16;
-    double *base = reinterpret_cast<double *>(smem_raw + lut_bytes) + (size_t)warp * warp_doubles;
+    double *base = reinterpret_cast<double *>(smem_raw + lut_bytes) + (size_t)(CTA ? 0 : warp) * warp_doubles;
     double *cur = base;
     double *nxt = base + cells;
     double *xs  = base + 2 * cells;                       // [m]
@@ -94,10 +149,10 @@ batched_kernel(BatchedArgs a, int warps_per_cta, int warp_doubles) {
     int32_t *cl = rl + m;                                 // [n] row labels
 
     double *Tg = a.T + lp * (int64_t)cells;
-    for (int k = lane; k < cells; k += 32) cur[k] = Tg[k];
-    for (int j = lane; j < m; j += 32) rl[j] = j;         // 'x1'..'xm'  :30
-    for (int i = lane; i < n; i += 32) cl[i] = m + i;     // 'y1'..'yn'  :31
-    __syncwarp();
+    for (int k = tl; k < cells; k += nl) cur[k] = Tg[k];
+    for (int j = tl; j < m; j += nl) rl[j] = j;           // 'x1'..'xm'  :30
+    for (int i = tl; i < n; i += nl) cl[i] = m + i;       // 'y1'..'yn'  :31
+    group_sync();
     const int fo = n * w1;                                // offset of the f row
     const double f0 = (m >= 1) ? cur[fo] : 0.0;           // self.function is never mutated (:29,:49)
     const double f1 = (m >= 2) ? cur[fo + 1] : 0.0;
@@ -109,50 +164,22 @@ batched_kernel(BatchedArgs a, int warps_per_cta, int warp_doubles) {
     for (;;) {
         if (snap) {
             double *sg = snap + (int64_t)npiv * cells;
-            for (int k = lane; k < cells; k += 32) sg[k] = cur[k];
+            for (int k = tl; k < cells; k += nl) sg[k] = cur[k];
         }
-        int r, c;
-        // ---- K1: phase-1 row (:72-76), its first positive cell (:81-85) ...
-        const int r1 = warp_first_index(n, lane, [&](int i) { return cur[i * w1 + m] < 0.0; });
-        if (r1 != SPX_NONE) {
-            c = warp_first_index(m, lane, [&](int j) { return cur[r1 * w1 + j] > 0.0; });
-            if (c == SPX_NONE) { status = SPX_INCORRECT; break; }                 // :88-89
-            r = r1;                                                               // :91
+        int r = -1, c = -1;
+        if (!CTA) {
+            status = warp_pick(cur, n, m, a.rule, lane, r, c);
         } else {
-            // ---- ... or the entering column from the f row (:94-98)
-            if (a.rule == SPX_RULE_REFERENCE) {
-                c = warp_first_index(m, lane, [&](int j) { return cur[fo + j] < 0.0; });
-            } else {   // Dantzig: most negative, lowest index on ties
-                unsigned long long best = ~0ull;
-                for (int j = lane; j < m; j += 32) {
-                    const double v = cur[fo + j];
-                    if (v < 0.0) { const unsigned long long k = orderable(v); best = k < best ? k : best; }
-                }
-#pragma unroll
-                for (int s = 16; s > 0; s >>= 1) {
-                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, s);
-                    best = o < best ? o : best;
-                }
-                c = (best == ~0ull) ? SPX_NONE
-                    : warp_first_index(m, lane, [&](int j) {
-                          const double v = cur[fo + j];
-                          return v < 0.0 && orderable(v) == best; });
+            if (warp == 0) {
+                const int st = warp_pick(cur, n, m, a.rule, lane, r, c);
+                if (lane == 0) { s_ctl[0] = st; s_ctl[1] = r; s_ctl[2] = c; }
             }
-            if (c == SPX_NONE) { status = SPX_OPTIMAL; break; }                   // :101-103
-            // ---- K2: the ratio scan (:107-136): lane-local fold, then ballots / redux across lanes
-            Ratio q = ratio_identity();
-            bool my_elig_nan = false;                    // is the ratio of MY first eligible row NaN?
-            for (int i = lane; i < n; i += 32) {
-                const double a_ic = cur[i * w1 + c], b_i = cur[i * w1 + m];
-                const bool first = (q.elig_row == SPX_NONE);
-                const bool is_nan = ratio_accumulate(q, i, a_ic, b_i);
-                if (first && q.elig_row != SPX_NONE) my_elig_nan = is_nan;
-            }
-            r = warp_ratio_decide(q, my_elig_nan, lane);
-            if (r < 0) { status = SPX_NOCONV; break; }                            // :138-139
+            __syncthreads();
+            status = s_ctl[0]; r = s_ctl[1]; c = s_ctl[2];
         }
+        if (status != SPX_PIVOT) break;
         if (npiv >= a.max_pivots) { status = SPX_CAP; break; }
-        if (trace && lane == 0) { trace[2 * npiv] = r; trace[2 * npiv + 1] = c; }
+        if (trace && tl == 0) { trace[2 * npiv] = r; trace[2 * npiv + 1] = c; }
 
         // ---- K3: out-of-place pivot (:149-177), all reads from `cur`; the four cell kinds
         // (:156 pivot row, :160 pivot column, :163 pivot cell, :173-175 the rest) differ only in
@@ -160,7 +187,7 @@ batched_kernel(BatchedArgs a, int warps_per_cta, int warp_doubles) {
         const double p = cur[r * w1 + c];
         const PivotDiv d = pivot_div_prepare(p);
         const double *prow = cur + r * w1;
-        for (int k = lane; k < cells; k += 32) {
+        for (int k = tl; k < cells; k += nl) {
             const int i = cell_i[k], j = cell_j[k];
             const double t = cur[k];
             const double ci = cur[i * w1 + c];
@@ -171,25 +198,25 @@ batched_kernel(BatchedArgs a, int warps_per_cta, int warp_doubles) {
             num = (pr && pc) ? 1.0 : num;
             nxt[k] = pivot_div(num, d);
         }
-        if (lane == 0) { const int32_t t = rl[c]; rl[c] = cl[r]; cl[r] = t; }     // :152
-        __syncwarp();
+        if (tl == 0) { const int32_t t = rl[c]; rl[c] = cl[r]; cl[r] = t; }      // :152
+        group_sync();                                      // (CTA: also orders s_ctl against the next pick)
         double *sw = cur; cur = nxt; nxt = sw;
         ++npiv;
     }
 
     // ---- epilogue: final table, labels, find_optimum()/f() (:48-68)
-    for (int k = lane; k < cells; k += 32) Tg[k] = cur[k];
-    for (int j = lane; j < m; j += 32) xs[j] = 0.0;
-    __syncwarp();
-    for (int i = lane; i < n; i += 32) {
+    for (int k = tl; k < cells; k += nl) Tg[k] = cur[k];
+    for (int j = tl; j < m; j += nl) xs[j] = 0.0;
+    group_sync();
+    for (int i = tl; i < n; i += nl) {
         const int lab = cl[i];
         if (lab < m) xs[lab] = cur[i * w1 + m];
     }
-    __syncwarp();
-    if (a.x) for (int j = lane; j < m; j += 32) a.x[lp * m + j] = xs[j];
-    if (a.rowlab) for (int j = lane; j < m; j += 32) a.rowlab[lp * m + j] = rl[j];
-    if (a.collab) for (int i = lane; i < n; i += 32) a.collab[lp * n + i] = cl[i];
-    if (lane == 0) {
+    group_sync();
+    if (a.x) for (int j = tl; j < m; j += nl) a.x[lp * m + j] = xs[j];
+    if (a.rowlab) for (int j = tl; j < m; j += nl) a.rowlab[lp * m + j] = rl[j];
+    if (a.collab) for (int i = tl; i < n; i += nl) a.collab[lp * n + i] = cl[i];
+    if (tl == 0) {
         a.status[lp] = status;
         a.npiv[lp] = npiv;
         if (a.obj) a.obj[lp] = (m >= 2) ? __dadd_rn(__dmul_rn(f0, xs[0]), __dmul_rn(f1, xs[1])) : 0.0;
@@ -206,6 +233,7 @@ size_t lut_bytes(int n, int m) {
     return (cells * 4 + 15) / 16 * 16;
 }
 constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr int64_t CTA_MODE_MIN_CELLS = 96;    // above this one CTA (not one warp) solves an LP
 
 } // namespace
 
@@ -221,6 +249,24 @@ cudaError_t solve_batched(double *T, int64_t B, int n, int m, int rule, int max_
     if (n > 65535 || m > 65534) return cudaErrorInvalidValue;
     const size_t wb = warp_bytes(n, m), lb = lut_bytes(n, m);
     if (lb + wb > SMEM_LIMIT) return cudaErrorInvalidValue;
+    const int64_t cells = (int64_t)n * (m + 1) + m;
+    BatchedArgs a{T, B, n, m, rule, max_pivots, x, obj, status, npiv, rowlab, collab, trace, snap};
+    static size_t configured[2] = {0, 0};
+    if (cells > CTA_MODE_MIN_CELLS) {
+        // one CTA per LP: 64 cells per warp, 2..8 warps
+        int warps = (int)((cells + 63) / 64);
+        warps = warps < 2 ? 2 : (warps > 8 ? 8 : warps);
+        const size_t smem = lb + wb;
+        if (smem > 48 * 1024 && smem > configured[1]) {
+            cudaError_t e = cudaFuncSetAttribute(batched_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)SMEM_LIMIT);
+            if (e != cudaSuccess) return e;
+            configured[1] = SMEM_LIMIT;
+        }
+        batched_kernel<true><<<(unsigned)B, warps * 32, smem, stream>>>(a, 1, (int)(wb / sizeof(double)));
+        spx_host::count_launch();
+        return cudaGetLastError();
+    }
     // warps per CTA: as many as fit ~48 KB (several CTAs per SM), at most 8, at least 1
     int wpc = (int)((48 * 1024 - lb) / wb);
     if (lb >= 48 * 1024) wpc = 0;
@@ -228,17 +274,14 @@ cudaError_t solve_batched(double *T, int64_t B, int n, int m, int rule, int max_
     if (wpc < 1) wpc = 1;
     if ((int64_t)wpc > B) wpc = (int)B;
     const size_t smem = lb + (size_t)wpc * wb;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(batched_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (smem > 48 * 1024 && smem > configured[0]) {
+        cudaError_t e = cudaFuncSetAttribute(batched_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)SMEM_LIMIT);
         if (e != cudaSuccess) return e;
-        configured = SMEM_LIMIT;
+        configured[0] = SMEM_LIMIT;
     }
-    BatchedArgs a{T, B, n, m, rule, max_pivots, x, obj, status, npiv, rowlab, collab, trace, snap};
     const int64_t ctas = (B + wpc - 1) / wpc;
-    batched_kernel<<<(unsigned)ctas, wpc * 32, smem, stream>>>(a, wpc, (int)(wb / sizeof(double)));
+    batched_kernel<false><<<(unsigned)ctas, wpc * 32, smem, stream>>>(a, wpc, (int)(wb / sizeof(double)));
     spx_host::count_launch();
     return cudaGetLastError();
 }
