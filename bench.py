@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 Workload (config.workload): cfg4 of BASELINE.json — the dense 16384 x 32768 fp64 LP
-D(16384, 32768, seed 0) of SURVEY.md §8d.  One *step* = PIVOTS_PER_STEP consecutive
+D(16384, 32768, seed 0) of SURVEY.md §8d.  One *step* = PIVOTS_PER_STEP (1000) consecutive
 pivots (pick + rank-1 update) of that tableau.  The full solve needs ~1e6 pivots, so
 timed steps simply continue the same solve; the pivot sequence of the run is checked
 against the golden prefix (tests/golden/cfg_digests.json) before anything is printed.
@@ -37,7 +37,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_ROWS, M_COLS, SEED = 16384, 32768, 0
-PIVOTS_PER_STEP = 200
+PIVOTS_PER_STEP = 1000
 METRIC = "pivots/sec (16k x 32k fp64 tableau)"
 UNIT = "pivots/s"
 
@@ -427,7 +427,7 @@ def run_ours(args):
             "config": config_dict(1), "clocks": clk.summary(),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * statistics.mean(e2e_t),
-                    "api": "SimplexMethod(pinned_rows, c).solve(max_pivots=200)"},
+                    "api": f"SimplexMethod(pinned_rows, c).solve(max_pivots={P})"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "hbm_gbs_whole_step": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9,
             "batched": batched, "l2_resident": resident,

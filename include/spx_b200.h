@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define SPX_ABI_VERSION 3
+#define SPX_ABI_VERSION 4
 
 /* status codes == the outcomes of pick_element(), simplex.py:70-141 */
 #define SPX_PIVOT       1   /* (True, r, c, e)                                   :91,:141 */
@@ -96,6 +96,7 @@ int64_t     spx_launch_count(int reset);
 #define SPX_OPT_PIPE_ORDER       3  /* pipelined kernel tile order: 0 chunked column-major, 1 interleaved row-major */
 #define SPX_OPT_PIPE_GRID        4  /* pipelined kernel CTAs (0 = one per SM) */
 #define SPX_OPT_TILED_ROWS       5  /* tiled kernel rows per tile (0 = auto; else a multiple of 8 <= 64) */
+#define SPX_OPT_FUSE_DEPTH       6  /* fused loop: pivots applied per pass over the body (0 = default 4, max 8) */
 int         spx_set_option(int32_t option, int64_t value);
 int64_t     spx_get_option(int32_t option);
 /* Device self-test of the hoisted-reciprocal division used by K3 against the
@@ -165,7 +166,12 @@ int spx_update(const double *d_Ain, double *d_Aout, const double *d_bin, double 
 #define SPX_LOOP_LOOKAHEAD 2
 #define SPX_LOOP_RESIDENT  3  /* ONE persistent cooperative kernel runs the whole loop (n <= 4095, both bodies in L2):
                                * every CTA prices the pivot redundantly, one grid barrier per pivot (csrc/spx_resident.cu) */
+#define SPX_LOOP_FUSED     4  /* F pivots per pass: one CTA prices the next F pivots from the stored table by replaying
+                               * the pending rank-1 updates on the O(n+m) cells the rules need, then ONE stream over
+                               * the body applies all F — 16 B of HBM traffic per cell per F pivots (csrc/spx_fused.cu).
+                               * Workspace: spx_fused_workspace_bytes(n, m).  Same pivots, same bits. */
 int64_t spx_solve_workspace_bytes(int32_t n);
+int64_t spx_fused_workspace_bytes(int32_t n, int32_t m);
 int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1,
               int32_t n, int32_t m, int64_t ld, int32_t rule,
               spx_state *d_state, double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab,

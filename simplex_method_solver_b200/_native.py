@@ -13,13 +13,14 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libspx_b200.so")
 
-ABI_VERSION = 3
-LOOP_AUTO, LOOP_CLASSIC, LOOP_LOOKAHEAD, LOOP_RESIDENT = 0, 1, 2, 3
+ABI_VERSION = 4
+LOOP_AUTO, LOOP_CLASSIC, LOOP_LOOKAHEAD, LOOP_RESIDENT, LOOP_FUSED = 0, 1, 2, 3, 4
 LOOP_MODES = {None: LOOP_AUTO, "auto": LOOP_AUTO, False: LOOP_CLASSIC, "classic": LOOP_CLASSIC,
-              True: LOOP_LOOKAHEAD, "lookahead": LOOP_LOOKAHEAD, "resident": LOOP_RESIDENT}
+              True: LOOP_LOOKAHEAD, "lookahead": LOOP_LOOKAHEAD, "resident": LOOP_RESIDENT,
+              "fused": LOOP_FUSED}
 PIVOT, OPTIMAL, INCORRECT, NOCONV, CAP, PEER_TIMEOUT = 1, 0, -1, -2, -3, -4
 RULE_REFERENCE, RULE_DANTZIG = 0, 1
-OPT_UPDATE_KERNEL, OPT_TILED_MIN_BLOCKS, OPT_PIPE_ORDER, OPT_PIPE_GRID = 1, 2, 3, 4
+OPT_UPDATE_KERNEL, OPT_TILED_MIN_BLOCKS, OPT_PIPE_ORDER, OPT_PIPE_GRID, OPT_TILED_ROWS, OPT_FUSE_DEPTH = 1, 2, 3, 4, 5, 6
 RULES = {"reference": RULE_REFERENCE, "bland": RULE_REFERENCE, "dantzig": RULE_DANTZIG}
 
 # the two ValueError texts of pick_element(), /root/reference/src/simplex.py:89,139
@@ -70,6 +71,7 @@ SIGNATURES = {
     "spx_pick": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),
     "spx_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spx_solve_workspace_bytes": (_i64, [_i32]),
+    "spx_fused_workspace_bytes": (_i64, [_i32, _i32]),
     "spx_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
                                  _i32, _i64, _i32, _vp, _i64, _pi32, _pi64, _vp]),
     "spx_extract": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

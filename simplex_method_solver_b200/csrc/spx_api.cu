@@ -31,6 +31,10 @@ cudaError_t extract(const double *, int, int, const int32_t *, const double *, d
 bool resident_fits(int, int, int64_t);
 cudaError_t resident_loop(double *, double *, double *, double *, int, int, int64_t, int, int64_t, spx_state *,
                           double *, int32_t *, int32_t *, int32_t *, cudaStream_t);
+int fuse_max();
+int64_t fused_workspace_bytes(int, int64_t);
+cudaError_t fused_pass(double *, double *, double *, double *, int, int, int64_t, int, int, spx_state *, void *,
+                       int32_t *, int32_t *, int32_t *, cudaStream_t);
 int64_t get_option(int);
 int     set_option(int, int64_t);
 cudaError_t selftest_division(const double *, const double *, int64_t, int64_t, unsigned long long *,
@@ -291,6 +295,10 @@ int side_ctx(SideCtx **out) {
 
 int64_t spx_solve_workspace_bytes(int32_t n) { return workspace_bytes(n); }
 
+int64_t spx_fused_workspace_bytes(int32_t n, int32_t m) {
+    return spx_launch::fused_workspace_bytes(n, spx_ld(m));
+}
+
 int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n, int32_t m, int64_t ld,
               int32_t rule, spx_state *d_state, double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab,
               int32_t *d_trace, int32_t chunk, int64_t stop_after, int32_t mode, void *d_work,
@@ -300,7 +308,7 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
     SPX_REQUIRE(d_state && d_colbuf && d_rowlab && d_collab, "spx_solve: null state/colbuf/labels");
     SPX_REQUIRE(chunk >= 1, "spx_solve: chunk must be >= 1");
     SPX_REQUIRE(rule == SPX_RULE_REFERENCE || rule == SPX_RULE_DANTZIG, "spx_solve: unknown rule %d", rule);
-    SPX_REQUIRE(mode >= SPX_LOOP_AUTO && mode <= SPX_LOOP_RESIDENT, "spx_solve: unknown mode %d", mode);
+    SPX_REQUIRE(mode >= SPX_LOOP_AUTO && mode <= SPX_LOOP_FUSED, "spx_solve: unknown mode %d", mode);
     if (mode == SPX_LOOP_AUTO) {
         // L2-resident tableaus: one persistent kernel; big ones: look-ahead streaming; else classic
         if (spx_launch::resident_fits(n, m, ld)) mode = SPX_LOOP_RESIDENT;
@@ -310,6 +318,10 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
     SPX_REQUIRE(mode != SPX_LOOP_RESIDENT || spx_launch::resident_fits(n, m, ld),
                 "spx_solve: the tableau does not fit the L2-resident loop (n <= 4095, 2 bodies <= 96 MB, cooperative launch)");
     SPX_REQUIRE(mode != SPX_LOOP_LOOKAHEAD || d_work != nullptr, "spx_solve: look-ahead needs a workspace");
+    SPX_REQUIRE(mode != SPX_LOOP_FUSED || (d_work != nullptr && ((uintptr_t)d_work & 127) == 0 &&
+                                           work_bytes >= spx_launch::fused_workspace_bytes(n, ld)),
+                "spx_solve: the fused loop needs a 128-byte aligned workspace of spx_fused_workspace_bytes(n, m) = %lld bytes",
+                (long long)spx_launch::fused_workspace_bytes(n, ld));
     const bool ahead = (mode == SPX_LOOP_LOOKAHEAD);
     SPX_REQUIRE(!ahead || (work_bytes >= workspace_bytes(n) && ((uintptr_t)d_work & 127) == 0),
                 "spx_solve: workspace must be 128-byte aligned and >= spx_solve_workspace_bytes(n) = %lld bytes",
@@ -332,12 +344,37 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
         w = carve(d_work, n);
     }
     int64_t done = 0;
+    if (mode == SPX_LOOP_FUSED) {
+        // the fused passes flip the ping-pong buffers once per PASS, not per pivot: the index of the
+        // current buffer travels in the device state while this call runs
+        const int64_t curbuf = hs.npiv & 1;
+        if (check(cudaMemcpyAsync(&d_state->reserved[0], &curbuf, sizeof(curbuf), cudaMemcpyHostToDevice, s), "cur")) return -1;
+        hs.reserved[0] = curbuf;
+    }
     bool priced = false;      // look-ahead: d_state/d_colbuf already hold the pick of the current table
     while (hs.status == SPX_PIVOT) {
         int64_t k = chunk;
         if (stop_after > 0 && stop_after - done < k) k = stop_after - done;
         if (k <= 0) break;
         const int64_t base = hs.npiv;
+        if (mode == SPX_LOOP_FUSED) {
+            // passes of F pivots: price F levels from the stored table (one CTA, O((n+m)F^2) work), then
+            // ONE stream over the body applies them all — 16 B of HBM traffic per cell per F pivots
+            int F = (int)spx_launch::get_option(SPX_OPT_FUSE_DEPTH);
+            if (F <= 0) F = 4;
+            if (F > spx_launch::fuse_max()) F = spx_launch::fuse_max();
+            int64_t left = k;
+            while (left > 0) {
+                const int Fp = (int)(left < F ? left : F);
+                if (check(spx_launch::fused_pass(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, Fp, d_state, d_work, d_rowlab,
+                                                 d_collab, d_trace, s), "fused pass launch")) return -1;
+                left -= Fp;
+            }
+            if (check(cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, s), "read state")) return -1;
+            if (check(cudaStreamSynchronize(s), "fused passes")) return -1;
+            done += hs.npiv - base;
+            continue;
+        }
         if (mode == SPX_LOOP_RESIDENT) {
             // one persistent cooperative launch applies up to k pivots (or all of them)
             if (stop_after <= 0) k = 1LL << 40;
@@ -388,6 +425,17 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
         if (check(cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, s), "read state")) return -1;
         if (check(cudaStreamSynchronize(s), "pivot chunk")) return -1;
         done += k;
+    }
+    if (mode == SPX_LOOP_FUSED) {
+        // restore the library-wide invariant "the current table is in buffer npiv & 1"
+        const int cur = (int)(hs.reserved[0] & 1), want = (int)(hs.npiv & 1);
+        if (cur != want) {
+            if (check(cudaMemcpyAsync(A[want], A[cur], (size_t)(n + 1) * ld * sizeof(double), cudaMemcpyDeviceToDevice, s), "table copy")) return -1;
+            if (check(cudaMemcpyAsync(b[want], b[cur], (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s), "b copy")) return -1;
+        }
+        const int64_t zero = 0;
+        if (check(cudaMemcpyAsync(&d_state->reserved[0], &zero, sizeof(zero), cudaMemcpyHostToDevice, s), "cur")) return -1;
+        if (check(cudaStreamSynchronize(s), "sync")) return -1;
     }
     if (h_status) *h_status = hs.status;
     if (h_npiv) *h_npiv = hs.npiv;

@@ -1,16 +1,16 @@
-// spx_batched.cu — K4: whole-LP solver for batches of independent small LPs,
-// one warp per LP, no communication: the loop of get_solution(),
-// /root/reference/src/simplex.py:179-199, with pick_element() (:70-141) and
-// recalculate_matrix() (:143-177) inlined.
+// spx_batched.cu — K4: whole-LP solver for batches of independent small LPs, no communication:
+// the loop of get_solution(), /root/reference/src/simplex.py:179-199, with pick_element()
+// (:70-141) and recalculate_matrix() (:143-177) inlined.
 //
-// The tableau of an LP lives in shared memory in the reference's own flat
-// layout (n rows of m+1 cells, then the f row with m cells) as two ping-pong
-// copies, because the reference pivots out of place (:149) and every cell of the
-// new table reads the OLD pivot row and column.  Lanes stride over the cells;
-// every decision is a warp ballot / shuffle reduction, so all 32 lanes always
-// take the same branch and no block-level barrier is needed after the prologue.
-// cfg1 (14 cells), cfg3 (26 cells) and Klee-Minty n=20 (440 cells, 2^20-1
-// strictly sequential pivots) all run through this kernel.
+// The tableau of an LP lives in shared memory in the reference's own flat layout (n rows of m+1
+// cells, then the f row with m cells) as two ping-pong copies, because the reference pivots out
+// of place (:149) and every cell of the new table reads the OLD pivot row and column.
+//   warp mode (<= 96 cells: cfg1 14 cells, cfg3 26 cells): one warp per LP, 8 LPs per CTA; every
+//       decision is a warp ballot / redux, all 32 lanes take the same branch, __syncwarp only.
+//   CTA mode (Klee-Minty n=20: 440 cells, 2^20-1 strictly sequential pivots): one CTA of 2..8 warps
+//       per LP; warp 0 prices the pivot, every warp updates 64 cells, two block barriers per pivot.
+// The four cell kinds of the pivot differ only in the numerator, so one division by the pivot
+// (pivot_div, reciprocal hoisted) serves them all without divergence.
 #include "spx_common.cuh"
 
 namespace {

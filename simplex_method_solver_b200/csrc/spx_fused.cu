@@ -1,0 +1,352 @@
+// spx_fused.cu — K6: F pivots per pass over the tableau (temporal blocking of the rank-1 updates).
+//
+// recalculate_matrix() (/root/reference/src/simplex.py:143-177) touches every cell once per pivot:
+// 16 B of HBM traffic per cell per pivot is the roofline of a pivot-at-a-time implementation.  But
+// what pick_element() (:70-141) needs to choose a pivot is only O(n + m) cells of the current
+// table — the b column, one row (f, or the phase-1 row), one column — plus, to apply it, the pivot
+// row and column.  Any single cell of the table "after i more pivots" can be evaluated lazily from
+// the stored table by replaying those i rank-1 updates on that one cell, with exactly the
+// reference's operation order and roundings (:156, :160, :163, :173-175).  So:
+//
+//   block_price_kernel  (one CTA) chooses the next F pivots from the MATERIALISED table k without
+//       touching the body: for level i it evaluates the needed row/column of the virtual table
+//       k+i through the i pending levels, runs the reference's selection rules on them, and records
+//       the level: (r_i, c_i, p_i), ROW_i = pivot row and COL_i = pivot column of table k+i.
+//   update_fused_kernel  streams the body ONCE and applies all F levels to every cell in registers:
+//       16 B of HBM traffic per cell per F pivots.  Same tiling as update_tiled_kernel; per level
+//       the 512-double slice of ROW_i and the slice of COL_i are staged in shared memory by TMA.
+//
+// Every cell still goes through the same sequence of separately rounded operations as in the
+// pivot-at-a-time path, so the pivot sequence and every bit of the table are unchanged
+// (tests/test_gpu_parity.py runs this loop against the same goldens and the oracle).
+#include "spx_block.cuh"
+
+namespace {
+
+using namespace spx;
+
+constexpr int FUSE_MAX       = 8;      // levels per pass at most
+constexpr int PRICE_THREADS  = 1024;
+constexpr int FUP_THREADS    = 256;
+constexpr int FUP_TC         = 2 * FUP_THREADS;
+constexpr int FUP_TR         = 32;     // rows per tile: the per-level row slices are amortised over 4 batches
+constexpr int FUP_UNROLL     = 8;
+constexpr int PRICE_BATCH    = 8;
+
+struct Level { int32_t r; int32_t c; double p; };
+struct alignas(128) PlanHeader {
+    int32_t f;          // levels to apply in this pass (0: nothing to do)
+    int32_t src;        // index (0/1) of the ping-pong buffer that holds the input table
+    int32_t pad[2];
+    Level   lvl[FUSE_MAX];
+};
+
+struct LevelDiv { int r, c; PivotDiv d; };
+
+// one pending level applied to the cell (t, j) whose current value is v
+__device__ __forceinline__ double apply_level(double v, int t, int j, const LevelDiv &L, double row_j, double col_t) {
+    if (t == L.r) return (j == L.c) ? pivot_cell_update(L.d.p) : pivot_div(-v, L.d);      // :163, :156
+    return (j == L.c) ? pivot_div(col_t, L.d) : cell_update(v, L.d, row_j, col_t);         // :160, :173-175
+}
+
+struct PriceArgs {
+    double *A[2];
+    double *b[2];
+    int n, m;
+    int64_t ld, cbd;        // leading dimension of the body / stride of the COLS planes
+    int rule, F;
+    spx_state *st;
+    PlanHeader *plan;
+    double *ROWS;           // [FUSE_MAX][ld]
+    double *COLS;           // [FUSE_MAX][cbd]
+    double *frow;           // [ld]   running f row of the virtual table
+    double *bvec;           // [n]    running b column of the virtual table
+    int32_t *rowlab, *collab, *trace;
+};
+
+__global__ void __launch_bounds__(PRICE_THREADS, 1)
+block_price_kernel(PriceArgs a) {
+    __shared__ Scratch s;
+    __shared__ LevelDiv s_lvl[FUSE_MAX];
+    __shared__ double s_scal[FUSE_MAX];          // per level: COL_l[t] (row scans) or ROW_l[c] (column build)
+    const int n = a.n, m = a.m, tid = threadIdx.x, nt = blockDim.x;
+    const int64_t ld = a.ld, cbd = a.cbd;
+
+    if (a.st->status != SPX_PIVOT) {             // sticky: nothing left to do in this pass
+        if (tid == 0) a.plan->f = 0;
+        return;
+    }
+    const int cur = (int)a.st->reserved[0] & 1;
+    const double *A = a.A[cur];
+    const int64_t npiv0 = a.st->npiv, cap = a.st->max_pivots;
+
+    // running copies of the b column and the f row of the virtual table
+    for (int t = tid; t < n; t += nt) a.bvec[t] = a.b[cur][t];
+    for (int j = tid; j < m; j += nt) a.frow[j] = A[(int64_t)n * ld + j];
+    __syncthreads();
+
+    int status = SPX_PIVOT, f = 0, last_r = -1, last_c = -1, phase1 = 0;
+    double last_p = 0.0;
+    for (int i = 0; i < a.F; ++i) {
+        // ---- K1: phase-1 row (:72-76) from the running b
+        const int rb = block_first_index_fn(n, [&](int t) { return a.bvec[t]; }, IsNeg(), s);
+        const int r1 = (rb == SPX_NONE) ? -1 : rb;
+        int c;
+        if (r1 >= 0) {
+            // the row r1 of the virtual table: the stored row replayed through the pending levels (:82-85)
+            if (tid < i) s_scal[tid] = a.COLS[(int64_t)tid * cbd + r1];
+            __syncthreads();
+            const double *row = A + (int64_t)r1 * ld;
+            c = block_first_index_fn(m, [&](int j) {
+                    double v = row[j];
+                    for (int l = 0; l < i; ++l) v = apply_level(v, r1, j, s_lvl[l], a.ROWS[(int64_t)l * ld + j], s_scal[l]);
+                    return v; }, IsPos(), s);
+        } else if (a.rule == SPX_RULE_REFERENCE) {
+            c = block_first_index_fn(m, [&](int j) { return a.frow[j]; }, IsNeg(), s);                 // :94-98
+        } else {                                     // Dantzig: most negative, lowest index on ties
+            unsigned long long best = ~0ull;
+            for (int j = tid; j < m; j += nt) {
+                const double v = a.frow[j];
+                if (v < 0.0) { const unsigned long long k = orderable(v); best = k < best ? k : best; }
+            }
+            best = block_min_u64(best, s);
+            int loc = SPX_NONE;
+            if (best != ~0ull)
+                for (int j = tid; j < m; j += nt) {
+                    const double v = a.frow[j];
+                    if (v < 0.0 && orderable(v) == best) { loc = j; break; }
+                }
+            c = block_min_int(loc, s);
+        }
+        if (c == SPX_NONE) { status = (r1 >= 0) ? SPX_INCORRECT : SPX_OPTIMAL; phase1 = (r1 >= 0); break; }
+
+        // ---- the entering column of the virtual table: strided gather + replay; ratio test (:107-136)
+        if (tid < i) s_scal[tid] = a.ROWS[(int64_t)tid * ld + c];
+        __syncthreads();
+        double *COLi = a.COLS + (int64_t)i * cbd;
+        Ratio q = ratio_identity();
+        const double *colp = A + c;
+        for (int base = 0; base <= n; base += nt * PRICE_BATCH) {
+            double v[PRICE_BATCH];
+#pragma unroll
+            for (int u = 0; u < PRICE_BATCH; ++u) {
+                const int t = base + u * nt + tid;
+                v[u] = (t <= n) ? colp[(int64_t)t * ld] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < PRICE_BATCH; ++u) {
+                const int t = base + u * nt + tid;
+                if (t <= n) {
+                    double w = v[u];
+                    for (int l = 0; l < i; ++l) w = apply_level(w, t, c, s_lvl[l], s_scal[l], a.COLS[(int64_t)l * cbd + t]);
+                    COLi[t] = w;
+                    if (r1 < 0 && t < n) ratio_accumulate(q, t, w, a.bvec[t]);
+                }
+            }
+        }
+        int r;
+        if (r1 >= 0) {
+            r = r1;                                                                                   // :91
+            __syncthreads();
+        } else {
+            q = block_ratio_reduce(q, s);
+            bool elig_nan = false;
+            if (q.elig_row != SPX_NONE) {
+                const double v = __ddiv_rn(a.bvec[q.elig_row], COLi[q.elig_row]);
+                elig_nan = (v != v);
+            }
+            r = ratio_decide(q, elig_nan);                                                            // :138-141
+            if (r < 0) { status = SPX_NOCONV; break; }
+        }
+        const double p = COLi[r];
+        if (npiv0 + i >= cap) { status = SPX_CAP; last_r = r; last_c = c; last_p = p; break; }
+
+        // ---- the pivot row of the virtual table (contiguous read + replay)
+        if (tid < i) s_scal[tid] = a.COLS[(int64_t)tid * cbd + r];
+        __syncthreads();
+        double *ROWi = a.ROWS + (int64_t)i * ld;
+        const double *rowp = A + (int64_t)r * ld;
+        for (int j = tid; j < m; j += nt) {
+            double v = rowp[j];
+            for (int l = 0; l < i; ++l) v = apply_level(v, r, j, s_lvl[l], a.ROWS[(int64_t)l * ld + j], s_scal[l]);
+            ROWi[j] = v;
+        }
+        for (int j = m + tid; j < ld; j += nt) ROWi[j] = 0.0;          // padding columns stay zero
+        // ---- record the level, then advance the running b column and f row by it
+        if (tid == 0) {
+            s_lvl[i].r = r; s_lvl[i].c = c; s_lvl[i].d = pivot_div_prepare(p);
+            a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p;
+            const int32_t tmp = a.rowlab[c]; a.rowlab[c] = a.collab[r]; a.collab[r] = tmp;            // :152
+            if (a.trace) { a.trace[2 * (npiv0 + i)] = r; a.trace[2 * (npiv0 + i) + 1] = c; }
+        }
+        __syncthreads();
+        const LevelDiv L = s_lvl[i];
+        const double br = a.bvec[r], fc = COLi[n];
+        __syncthreads();
+        for (int t = tid; t < n; t += nt) {
+            const double bt = a.bvec[t];
+            a.bvec[t] = (t == r) ? pivot_div(-bt, L.d) : cell_update(bt, L.d, br, COLi[t]);
+        }
+        for (int j = tid; j < m; j += nt) {
+            const double fj = a.frow[j];
+            a.frow[j] = (j == c) ? pivot_div(fc, L.d) : cell_update(fj, L.d, ROWi[j], fc);
+        }
+        __syncthreads();
+        f = i + 1; last_r = r; last_c = c; last_p = p; phase1 = (r1 >= 0);
+    }
+
+    // ---- publish: the b column after f levels, the plan header, the state
+    if (f > 0) for (int t = tid; t < n; t += nt) a.b[cur ^ 1][t] = a.bvec[t];
+    if (tid == 0) {
+        a.plan->f = f;
+        a.plan->src = cur;
+        spx_state *st = a.st;
+        st->status = status; st->r = last_r; st->c = last_c; st->p = last_p;
+        st->npiv = npiv0 + f; st->phase1 = phase1; st->slot = 0;
+        st->hint_tag[0] = st->hint_tag[1] = -1;
+        st->reserved[0] = (f > 0) ? (cur ^ 1) : cur;
+    }
+}
+
+// ---- the fused streaming update: one pass over the body applies plan->f levels -----------------
+struct FusedSmem {
+    double rows[FUSE_MAX][FUP_TC];      // per level: slice of ROW_l for this column tile
+    double cols[FUSE_MAX][FUP_TR];      // per level: slice of COL_l for this row tile
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(FUP_THREADS, MINB)
+update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd,
+                    const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
+                    const double *__restrict__ COLS) {
+    const int f = plan->f;
+    if (f <= 0) return;
+    extern __shared__ __align__(128) unsigned char fus_raw[];
+    FusedSmem &sm = *reinterpret_cast<FusedSmem *>(fus_raw);
+    __shared__ LevelDiv s_lvl[FUSE_MAX];
+    __shared__ alignas(8) uint64_t s_bar;
+
+    const int src = plan->src;
+    const double *__restrict__ Ain = src ? A1 : A0;
+    double *__restrict__ Aout = src ? A0 : A1;
+
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.x * FUP_TC;
+    const int i0 = blockIdx.y * FUP_TR;
+    const int rows = min(FUP_TR, n + 1 - i0);
+    const uint32_t row_bytes = (uint32_t)(min((int64_t)FUP_TC, ld - j0) * 8);
+    const uint32_t col_bytes = (uint32_t)(FUP_TR * 8);                 // COLS planes are padded to whole tiles
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&s_bar, (uint32_t)f * (row_bytes + col_bytes));
+        for (int l = 0; l < f; ++l) {
+            bulk_g2s(sm.rows[l], ROWS + (int64_t)l * ld + j0, row_bytes, &s_bar);
+            bulk_g2s(sm.cols[l], COLS + (int64_t)l * cbd + i0, col_bytes, &s_bar);
+        }
+    }
+    if (tid < f) {
+        s_lvl[tid].r = plan->lvl[tid].r;
+        s_lvl[tid].c = plan->lvl[tid].c;
+        s_lvl[tid].d = pivot_div_prepare(plan->lvl[tid].p);
+    }
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+
+    const int j = j0 + 2 * tid;
+    if (j >= m) return;
+    // CTA-uniform: does any level's pivot row / column cross this tile?
+    bool special = false;
+    for (int l = 0; l < f; ++l) {
+        const int rl = s_lvl[l].r, cl = s_lvl[l].c;
+        special = special || (rl >= i0 && rl < i0 + rows) || (cl >= j0 && cl < j0 + FUP_TC);
+    }
+    const double *srcp = Ain + (int64_t)i0 * ld + j;
+    double *dstp = Aout + (int64_t)i0 * ld + j;
+    for (int ii = 0; ii < rows; ii += FUP_UNROLL) {
+        double2 t[FUP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FUP_UNROLL; ++u)
+            if (ii + u < rows) t[u] = ld_stream(srcp + (int64_t)(ii + u) * ld);
+        if (!special) {
+            for (int l = 0; l < f; ++l) {
+                const double2 rj = *reinterpret_cast<const double2 *>(&sm.rows[l][2 * tid]);
+                const PivotDiv d = s_lvl[l].d;
+#pragma unroll
+                for (int u = 0; u < FUP_UNROLL; ++u) {
+                    const double ci = sm.cols[l][ii + u];
+                    t[u].x = cell_update(t[u].x, d, rj.x, ci);
+                    t[u].y = cell_update(t[u].y, d, rj.y, ci);
+                }
+            }
+        } else {
+            for (int l = 0; l < f; ++l) {
+                const double2 rj = *reinterpret_cast<const double2 *>(&sm.rows[l][2 * tid]);
+                const LevelDiv L = s_lvl[l];
+#pragma unroll
+                for (int u = 0; u < FUP_UNROLL; ++u) {
+                    const int ti = i0 + ii + u;
+                    const double ci = sm.cols[l][ii + u];
+                    t[u].x = apply_level(t[u].x, ti, j, L, rj.x, ci);
+                    t[u].y = apply_level(t[u].y, ti, j + 1, L, rj.y, ci);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FUP_UNROLL; ++u)
+            if (ii + u < rows) st_stream(dstp + (int64_t)(ii + u) * ld, t[u]);
+    }
+}
+
+} // namespace
+
+namespace spx_launch {
+
+int64_t colbuf_doubles(int n);
+
+int fuse_max() { return FUSE_MAX; }
+
+static inline int64_t align128(int64_t v) { return (v + 127) / 128 * 128; }
+
+// workspace: plan header | ROWS[FUSE_MAX][ld] | COLS[FUSE_MAX][cbd] | frow[ld] | bvec[n]
+int64_t fused_workspace_bytes(int n, int64_t ld) {
+    const int64_t cbd = colbuf_doubles(n);
+    return align128(sizeof(PlanHeader)) + align128(FUSE_MAX * ld * 8) + align128(FUSE_MAX * cbd * 8) +
+           align128(ld * 8) + align128(((int64_t)n + 16) * 8);
+}
+
+// one pass: price up to F pivots from the materialised table, then stream the body once
+cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, int m, int64_t ld, int rule,
+                       int F, spx_state *st, void *work, int32_t *rowlab, int32_t *collab, int32_t *trace,
+                       cudaStream_t stream) {
+    if (F < 1) F = 1;
+    if (F > FUSE_MAX) F = FUSE_MAX;
+    const int64_t cbd = colbuf_doubles(n);
+    char *p = static_cast<char *>(work);
+    PlanHeader *plan = reinterpret_cast<PlanHeader *>(p);       p += align128(sizeof(PlanHeader));
+    double *ROWS = reinterpret_cast<double *>(p);               p += align128(FUSE_MAX * ld * 8);
+    double *COLS = reinterpret_cast<double *>(p);               p += align128(FUSE_MAX * cbd * 8);
+    double *frow = reinterpret_cast<double *>(p);               p += align128(ld * 8);
+    double *bvec = reinterpret_cast<double *>(p);
+    PriceArgs a;
+    a.A[0] = A0; a.A[1] = A1; a.b[0] = b0; a.b[1] = b1;
+    a.n = n; a.m = m; a.ld = ld; a.cbd = cbd; a.rule = rule; a.F = F;
+    a.st = st; a.plan = plan; a.ROWS = ROWS; a.COLS = COLS; a.frow = frow; a.bvec = bvec;
+    a.rowlab = rowlab; a.collab = collab; a.trace = trace;
+    block_price_kernel<<<1, PRICE_THREADS, 0, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    static bool configured = false;
+    if (!configured) {
+        e = cudaFuncSetAttribute(update_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(FusedSmem));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid((unsigned)((m + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + FUP_TR - 1) / FUP_TR));
+    update_fused_kernel<2><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS);
+    spx_host::count_launch(2);
+    return cudaGetLastError();
+}
+
+} // namespace spx_launch

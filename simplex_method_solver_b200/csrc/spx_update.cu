@@ -433,6 +433,7 @@ int set_option(int key, int64_t value) {
     case SPX_OPT_PIPE_ORDER:       if (value < 0 || value > 1) return -1; break;
     case SPX_OPT_PIPE_GRID:        if (value < 0 || value > 4096) return -1; break;
     case SPX_OPT_TILED_ROWS:       if (value < 0 || value > UPD_TR_MAX || value % 8) return -1; break;
+    case SPX_OPT_FUSE_DEPTH:       if (value < 0 || value > 8) return -1; break;
     default: return -1;
     }
     g_opt[key] = value;

@@ -73,8 +73,8 @@ class DeviceTableau:
             self.obj = torch.empty(2, dtype=torch.float64, device=dev)
             self.trace = (torch.empty((trace_capacity, 2), dtype=torch.int32, device=dev)
                           if trace_capacity > 0 else None)
-            self.work = torch.zeros(int(L.spx_solve_workspace_bytes(self.n)) // 8, dtype=torch.float64,
-                                    device=dev)
+            wbytes = max(int(L.spx_solve_workspace_bytes(self.n)), int(L.spx_fused_workspace_bytes(self.n, self.m)))
+            self.work = torch.zeros(wbytes // 8, dtype=torch.float64, device=dev)
         self.trace_capacity = int(trace_capacity)
         self.max_pivots = int(max_pivots)
         self._keepalive = None

@@ -99,7 +99,8 @@ def test_problem_files_feed_the_batched_solver(spx):
 
 
 # --------------------------------------------------------------------------- all golden cases
-@pytest.mark.parametrize("lookahead,chunk", [(False, 7), (True, 7), (True, 4), (True, 1), ("resident", 7), (None, 5)])
+@pytest.mark.parametrize("lookahead,chunk", [(False, 7), (True, 7), (True, 4), (True, 1), ("resident", 7), (None, 5),
+                                             ("fused", 7), ("fused", 3)])
 def test_all_reference_cases_streaming_solver(spx, ref_cases, lookahead, chunk):
     """solve(): device-side loop, classic (pick k, update k, ...) and look-ahead (pivot k+1 priced
     from table k on a side stream while update k runs); trace, ending, labels, final table bits."""
@@ -175,7 +176,7 @@ def test_step_api_matches_oracle(spx):
                 break
 
 
-@pytest.mark.parametrize("mode", [True, "resident"])
+@pytest.mark.parametrize("mode", [True, "resident", "fused"])
 def test_lookahead_state_feeds_the_step_api_and_resumes(spx, mode):
     """A look-ahead / resident solve stopped by the cap leaves a state the step API and a resumed solve continue from."""
     rows, c = W.dense_lp(40, 70, 9)
@@ -196,7 +197,7 @@ def test_lookahead_state_feeds_the_step_api_and_resumes(spx, mode):
     assert sol.x.tobytes() == ref.x.tobytes()
 
 
-@pytest.mark.parametrize("lookahead", [False, True, "resident"])
+@pytest.mark.parametrize("lookahead", [False, True, "resident", "fused"])
 def test_dantzig_rule_modes_agree(spx, lookahead):
     """rule='dantzig' (extension, not reference behaviour): classic and look-ahead give one trace."""
     rows, c = W.dense_lp(30, 50, 4)
@@ -258,9 +259,11 @@ def test_pick_update_bit_exact_ragged_shapes(spx, n, m):
         assert dev.read_state().npiv == npiv
 
 
+@pytest.mark.parametrize("mode", ["resident", "fused"])
 @pytest.mark.parametrize("n,m", [(1, 2), (3, 1), (7, 15), (9, 17), (64, 512), (65, 513), (130, 1030), (257, 100), (40, 2049)])
-def test_resident_loop_bit_exact_ragged_shapes(spx, n, m):
-    """The persistent L2-resident loop in steps of 1..3 pivots vs the oracle, whole table each time."""
+def test_resident_and_fused_loops_bit_exact_ragged_shapes(spx, n, m, mode):
+    """The persistent L2-resident loop and the F-pivots-per-pass fused loop in steps of 1..9 pivots vs the
+    oracle, whole table each time (odd step counts leave the table in either ping-pong buffer)."""
     rng = np.random.default_rng(n * 31 + m)
     rows, c = W.dense_lp(n, m, seed=n + 2 * m)
     rows[rng.random(rows.shape) < 0.05] = 0.0
@@ -268,7 +271,7 @@ def test_resident_loop_bit_exact_ragged_shapes(spx, n, m):
     dev.load(rows, c, max_pivots=64)
     T = flat_of(rows, c)
     npiv = 0
-    for k in (1, 2, 3, 1, 3):
+    for k in (1, 2, 3, 1, 9, 5):
         want = []
         for _ in range(k):
             st, r, cc, e = oracle.pick(T, n, m)
@@ -276,17 +279,20 @@ def test_resident_loop_bit_exact_ragged_shapes(spx, n, m):
                 break
             want.append([r, cc])
             T = oracle.update(T, n, m, r, cc)
-        status, got = dev.solve(stop_after=k, lookahead="resident")
+        status, got = dev.solve(stop_after=k, lookahead=mode)
         assert got == npiv + len(want)
         assert dev.trace[npiv:got].cpu().numpy().tolist() == want
         npiv = got
         assert np.array_equal(bits(dev.export_flat(npiv)), bits(T)), (n, m, npiv)
         st, r, cc, e = oracle.pick(T, n, m)
+        if mode == "fused" and status == oracle.PIVOT and st != oracle.PIVOT and len(want) == k:
+            continue                                     # fused stops unpriced: the next call reports the ending
         assert status == st
         if st != oracle.PIVOT:
             break
-        s_ = dev.read_state()
-        assert (s_.r, s_.c, s_.p) == (r, cc, e)          # priced, not yet applied
+        if mode == "resident":
+            s_ = dev.read_state()
+            assert (s_.r, s_.c, s_.p) == (r, cc, e)      # priced, not yet applied
 
 
 def test_ratio_scan_special_values(spx):
@@ -479,7 +485,7 @@ def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookah
 
 
 # --------------------------------------------------------------------------- BASELINE configs
-@pytest.mark.parametrize("lookahead", [False, True, "resident"])
+@pytest.mark.parametrize("lookahead", [False, True, "resident", "fused"])
 def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests, lookahead):
     g = cfg_digests["cfg2"]
     rows, c = W.dense_lp(1000, 2000, 0)
@@ -537,7 +543,7 @@ def test_cfg5_klee_minty(spx, cfg_digests, n):
     assert res.x[0, n - 1] == float(5 ** n) and (res.x[0, : n - 1] == 0).all()
 
 
-@pytest.mark.parametrize("lookahead", [False, True, "resident"])
+@pytest.mark.parametrize("lookahead", [False, True, "resident", "fused"])
 def test_cfg5_klee_minty10_streaming_equals_batched(spx, cfg_digests, lookahead):
     rows, c = W.klee_minty(10)
     sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
@@ -548,20 +554,20 @@ def test_cfg5_klee_minty10_streaming_equals_batched(spx, cfg_digests, lookahead)
 
 
 def test_cfg4_16k_x_32k_prefix(spx, cfg_digests):
-    """The 4.3 GB tableau: first 200 pivots against the oracle-generated golden prefix."""
+    """The 4.3 GB tableau: first 800 pivots against the oracle-generated golden prefix."""
     g = cfg_digests["cfg4"]
     n, m = 16384, 32768
     rows, c = W.dense_lp(n, m, 0)
     assert W.input_digest(rows, c) == g["input_sha256"]
-    dev = spx.engine.DeviceTableau(n, m, trace_capacity=256)
-    dev.load(rows, c, max_pivots=256)       # look-ahead prices pivot 201: keep the cap out of the way
+    dev = spx.engine.DeviceTableau(n, m, trace_capacity=1024)
+    dev.load(rows, c, max_pivots=1024)      # look-ahead prices pivot 801: keep the cap out of the way
     del rows
     dev.pick(0)
     s = dev.read_state()
     assert (s.r, s.c) == tuple(g["trace"][0]) and float(s.p).hex() == g["first_pivot_value"]
     done = 0
-    for mark in (16, 50, 100, 200):
-        status, npiv = dev.solve(chunk=mark - done, stop_after=mark - done)
+    for mark in (16, 50, 100, 200, 800):
+        status, npiv = dev.solve(chunk=min(mark - done, 256), stop_after=mark - done)
         done = mark
         assert npiv == mark and status == spx.N.PIVOT
         tr = dev.trace[:mark].cpu().numpy()
