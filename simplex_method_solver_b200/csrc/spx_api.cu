@@ -33,8 +33,8 @@ cudaError_t resident_loop(double *, double *, double *, double *, int, int, int6
                           double *, int32_t *, int32_t *, int32_t *, cudaStream_t);
 int fuse_max();
 int64_t fused_workspace_bytes(int, int64_t);
-cudaError_t fused_pass(double *, double *, double *, double *, int, int, int64_t, int, int, spx_state *, void *,
-                       int32_t *, int32_t *, int32_t *, cudaStream_t);
+cudaError_t fused_pass(double *, double *, double *, double *, int, int, int64_t, int, int, int, int, spx_state *,
+                       void *, int32_t *, int32_t *, int32_t *, cudaStream_t);
 int64_t get_option(int);
 int     set_option(int, int64_t);
 cudaError_t selftest_division(const double *, const double *, int64_t, int64_t, unsigned long long *,
@@ -366,7 +366,9 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
             int64_t left = k;
             while (left > 0) {
                 const int Fp = (int)(left < F ? left : F);
-                if (check(spx_launch::fused_pass(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, Fp, d_state, d_work, d_rowlab,
+                if (check(spx_launch::fused_pass(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, Fp,
+                                                 (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS),
+                                                 (int)spx_launch::get_option(SPX_OPT_FUSE_PRICING), d_state, d_work, d_rowlab,
                                                  d_collab, d_trace, s), "fused pass launch")) return -1;
                 left -= Fp;
             }

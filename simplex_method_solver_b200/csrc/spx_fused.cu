@@ -19,7 +19,11 @@
 // Every cell still goes through the same sequence of separately rounded operations as in the
 // pivot-at-a-time path, so the pivot sequence and every bit of the table are unchanged
 // (tests/test_gpu_parity.py runs this loop against the same goldens and the oracle).
+#include <cooperative_groups.h>
+
 #include "spx_block.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -208,6 +212,206 @@ block_price_kernel(PriceArgs a) {
     }
 }
 
+// ---- the same pricing spread over the whole GPU (cooperative launch) ---------------------------
+// block_price_kernel is strictly sequential work for ONE CTA (0.3 ms at F = 4, 0.8 ms at F = 8 on
+// cfg4) while the rest of the GPU idles between two fused passes.  Here every O(n) / O(m) loop is
+// dealt out over all CTAs (one element per thread at cfg4) and the two decisions of a level — the
+// entering column (an index min) and the leaving row (the ratio fold) — go through global scratch and
+// a grid barrier: two barriers per level, ~10 us per level.  Data written by other CTAs during the
+// kernel is read with ld.global.cg (L1 is not coherent across SMs).
+struct CoopScratch {
+    int   idx[FUSE_MAX + 1][4];                 // per level: [first negative b, entering column, phase-1 column, -]
+    unsigned long long key[FUSE_MAX + 1];       // Dantzig: most negative running f value (orderable image)
+};
+
+struct CoopArgs {
+    PriceArgs  a;
+    double    *bv[2];          // running b column, ping-pong per level
+    CoopScratch *cs;
+    Ratio     *part;           // [FUSE_MAX][gridDim.x] ratio partials
+};
+
+__global__ void __launch_bounds__(256, 1)
+coop_price_kernel(CoopArgs ca) {
+    cg::grid_group grid = cg::this_grid();
+    const PriceArgs &a = ca.a;
+    __shared__ Scratch s;
+    __shared__ LevelDiv s_lvl[FUSE_MAX];
+    __shared__ double s_scal[FUSE_MAX];
+    const int n = a.n, m = a.m, tid = threadIdx.x;
+    const int G = gridDim.x, gtid = blockIdx.x * blockDim.x + tid, gn = G * blockDim.x;
+    const int64_t ld = a.ld, cbd = a.cbd;
+
+    if (a.st->status != SPX_PIVOT) {             // uniform over the grid: nobody reaches a barrier
+        if (gtid == 0) a.plan->f = 0;
+        return;
+    }
+    const int cur = (int)a.st->reserved[0] & 1;
+    const double *A = a.A[cur];
+    const int64_t npiv0 = a.st->npiv, cap = a.st->max_pivots;
+
+    if (blockIdx.x == 0)
+        for (int k = tid; k < (FUSE_MAX + 1) * 4; k += blockDim.x) {
+            ca.cs->idx[k / 4][k % 4] = SPX_NONE;
+            if (k % 4 == 0) ca.cs->key[k / 4] = ~0ull;
+        }
+    grid.sync();
+
+    int status = SPX_PIVOT, f = 0, last_r = -1, last_c = -1, phase1 = 0;
+    double last_p = 0.0;
+    for (int i = 0; i <= a.F; ++i) {
+        // ---------------- phase A: bring the running b column / f row to the virtual table k+i (for
+        // i > 0 this also builds ROW_{i-1}, the pivot row of the level just chosen) and fold the
+        // first-negative searches of level i into the same sweep
+        double *bout = ca.bv[i & 1];
+        int bneg = SPX_NONE, fneg = SPX_NONE;
+        unsigned long long fkey = ~0ull;
+        if (i == 0) {
+            for (int t = gtid; t < n; t += gn) { const double v = a.b[cur][t]; bout[t] = v; if (v < 0.0) bneg = min(bneg, t); }
+            for (int j = gtid; j < m; j += gn) {
+                const double v = A[(int64_t)n * ld + j];
+                a.frow[j] = v;
+                if (v < 0.0) { fneg = min(fneg, j); const unsigned long long k = orderable(v); fkey = k < fkey ? k : fkey; }
+            }
+        } else {
+            const LevelDiv L = s_lvl[i - 1];
+            const double *bin = ca.bv[(i - 1) & 1];
+            const double *COLL = a.COLS + (int64_t)(i - 1) * cbd;
+            const double br = __ldcg(bin + L.r), fc = __ldcg(COLL + n);
+            for (int t = gtid; t < n; t += gn) {
+                const double bt = __ldcg(bin + t);
+                const double v = (t == L.r) ? pivot_div(-bt, L.d) : cell_update(bt, L.d, br, __ldcg(COLL + t));
+                bout[t] = v;
+                if (v < 0.0) bneg = min(bneg, t);
+            }
+            if (tid < i - 1) s_scal[tid] = __ldcg(a.COLS + (int64_t)tid * cbd + L.r);
+            __syncthreads();
+            double *ROWL = a.ROWS + (int64_t)(i - 1) * ld;
+            const double *rowp = A + (int64_t)L.r * ld;
+            for (int j = gtid; j < ld; j += gn) {
+                if (j >= m) { ROWL[j] = 0.0; continue; }                // padding columns stay zero
+                double rv = rowp[j];
+                for (int l = 0; l < i - 1; ++l)
+                    rv = apply_level(rv, L.r, j, s_lvl[l], __ldcg(a.ROWS + (int64_t)l * ld + j), s_scal[l]);
+                ROWL[j] = rv;
+                const double fj = a.frow[j];                             // j is owned by this thread all kernel long
+                const double v = (j == L.c) ? pivot_div(fc, L.d) : cell_update(fj, L.d, rv, fc);
+                a.frow[j] = v;
+                if (v < 0.0) { fneg = min(fneg, j); const unsigned long long k = orderable(v); fkey = k < fkey ? k : fkey; }
+            }
+        }
+        if (i == a.F) { f = a.F; break; }                                // every level of the pass is chosen
+        bneg = block_min_int(bneg, s);
+        fneg = block_min_int(fneg, s);
+        if (tid == 0) {
+            if (bneg != SPX_NONE) atomicMin(&ca.cs->idx[i][0], bneg);
+            if (fneg != SPX_NONE) atomicMin(&ca.cs->idx[i][1], fneg);
+        }
+        if (a.rule == SPX_RULE_DANTZIG) {
+            fkey = block_min_u64(fkey, s);
+            if (tid == 0 && fkey != ~0ull) atomicMin(&ca.cs->key[i], fkey);
+        }
+        grid.sync();
+        const int rb = __ldcg(&ca.cs->idx[i][0]);
+        const int r1 = (rb == SPX_NONE) ? -1 : rb;
+        int c = __ldcg(&ca.cs->idx[i][1]);
+        if (r1 >= 0) {
+            // phase-1: first positive cell of the virtual row r1 (:82-85)
+            if (tid < i) s_scal[tid] = __ldcg(a.COLS + (int64_t)tid * cbd + r1);
+            __syncthreads();
+            const double *row = A + (int64_t)r1 * ld;
+            int loc = SPX_NONE;
+            for (int j = gtid; j < m; j += gn) {
+                double v = row[j];
+                for (int l = 0; l < i; ++l) v = apply_level(v, r1, j, s_lvl[l], __ldcg(a.ROWS + (int64_t)l * ld + j), s_scal[l]);
+                if (v > 0.0) { loc = j; break; }
+            }
+            loc = block_min_int(loc, s);
+            if (tid == 0 && loc != SPX_NONE) atomicMin(&ca.cs->idx[i][2], loc);
+            grid.sync();
+            c = __ldcg(&ca.cs->idx[i][2]);
+        } else if (a.rule == SPX_RULE_DANTZIG && c != SPX_NONE) {
+            // lowest index among the columns that attain the most negative value
+            const unsigned long long best = __ldcg(&ca.cs->key[i]);
+            int loc = SPX_NONE;
+            for (int j = gtid; j < m; j += gn) {
+                const double v = a.frow[j];
+                if (v < 0.0 && orderable(v) == best) { loc = j; break; }
+            }
+            loc = block_min_int(loc, s);
+            if (tid == 0 && loc != SPX_NONE) atomicMin(&ca.cs->idx[i][2], loc);
+            grid.sync();
+            c = __ldcg(&ca.cs->idx[i][2]);
+        }
+        if (c == SPX_NONE) { status = (r1 >= 0) ? SPX_INCORRECT : SPX_OPTIMAL; phase1 = (r1 >= 0); f = i; break; }
+
+        // ---------------- phase B: the entering column of the virtual table + the ratio fold (:107-136)
+        if (tid < i) s_scal[tid] = __ldcg(a.ROWS + (int64_t)tid * ld + c);
+        __syncthreads();
+        double *COLi = a.COLS + (int64_t)i * cbd;
+        Ratio q = ratio_identity();
+        for (int t = gtid; t <= n; t += gn) {
+            double w = A[(int64_t)t * ld + c];
+            for (int l = 0; l < i; ++l) w = apply_level(w, t, c, s_lvl[l], s_scal[l], __ldcg(a.COLS + (int64_t)l * cbd + t));
+            COLi[t] = w;
+            if (r1 < 0 && t < n) ratio_accumulate(q, t, w, bout[t]);     // bout[t] was written by this very thread
+        }
+        q = block_ratio_reduce(q, s);
+        Ratio *part = ca.part + (int64_t)i * G;
+        if (tid == 0) part[blockIdx.x] = q;
+        grid.sync();
+        int r;
+        if (r1 >= 0) {
+            r = r1;                                                      // :91
+        } else {
+            Ratio z = ratio_identity();
+            for (int k = tid; k < G; k += blockDim.x) {
+                Ratio y;
+                y.neg_val = __ldcg(&part[k].neg_val); y.neg_row = __ldcg(&part[k].neg_row);
+                y.zero_row = __ldcg(&part[k].zero_row); y.elig_row = __ldcg(&part[k].elig_row);
+                z = ratio_merge(z, y);
+            }
+            z = block_ratio_reduce(z, s);
+            bool elig_nan = false;
+            if (z.elig_row != SPX_NONE) {
+                const double v = __ddiv_rn(__ldcg(bout + z.elig_row), __ldcg(COLi + z.elig_row));
+                elig_nan = (v != v);
+            }
+            r = ratio_decide(z, elig_nan);                               // :138-141
+            if (r < 0) { status = SPX_NOCONV; f = i; break; }
+        }
+        const double p = __ldcg(COLi + r);
+        if (npiv0 + i >= cap) { status = SPX_CAP; last_r = r; last_c = c; last_p = p; f = i; break; }
+        __syncthreads();
+        if (tid == 0) {
+            s_lvl[i].r = r; s_lvl[i].c = c; s_lvl[i].d = pivot_div_prepare(p);
+            if (blockIdx.x == 0) {
+                a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p;
+                const int32_t tmp = a.rowlab[c]; a.rowlab[c] = a.collab[r]; a.collab[r] = tmp;        // :152
+                if (a.trace) { a.trace[2 * (npiv0 + i)] = r; a.trace[2 * (npiv0 + i) + 1] = c; }
+            }
+        }
+        __syncthreads();
+        last_r = r; last_c = c; last_p = p; phase1 = (r1 >= 0);
+    }
+
+    // ---------------- publish: b after f levels (phase A of iteration f wrote it), plan, state
+    if (f > 0) {
+        grid.sync();
+        const double *bfin = ca.bv[f & 1];
+        for (int t = gtid; t < n; t += gn) a.b[cur ^ 1][t] = __ldcg(bfin + t);
+    }
+    if (gtid == 0) {
+        a.plan->f = f;
+        a.plan->src = cur;
+        spx_state *st = a.st;
+        st->status = status; st->r = last_r; st->c = last_c; st->p = last_p;
+        st->npiv = npiv0 + f; st->phase1 = phase1; st->slot = 0;
+        st->hint_tag[0] = st->hint_tag[1] = -1;
+        st->reserved[0] = (f > 0) ? (cur ^ 1) : cur;
+    }
+}
+
 // ---- the fused streaming update: one pass over the body applies plan->f levels -----------------
 struct FusedSmem {
     double rows[FUSE_MAX][FUP_TC];      // per level: slice of ROW_l for this column tile
@@ -269,14 +473,34 @@ update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cb
         for (int u = 0; u < FUP_UNROLL; ++u)
             if (ii + u < rows) t[u] = ld_stream(srcp + (int64_t)(ii + u) * ld);
         if (!special) {
+            // steady state: F dependent rank-1 updates per cell, guards accumulated, no branches
+            bool ok = true;
             for (int l = 0; l < f; ++l) {
                 const double2 rj = *reinterpret_cast<const double2 *>(&sm.rows[l][2 * tid]);
                 const PivotDiv d = s_lvl[l].d;
+                ok = ok && d.ok;
 #pragma unroll
                 for (int u = 0; u < FUP_UNROLL; ++u) {
                     const double ci = sm.cols[l][ii + u];
-                    t[u].x = cell_update(t[u].x, d, rj.x, ci);
-                    t[u].y = cell_update(t[u].y, d, rj.y, ci);
+                    t[u].x = cell_update_unchecked(t[u].x, d, rj.x, ci, ok);
+                    t[u].y = cell_update_unchecked(t[u].y, d, rj.y, ci, ok);
+                }
+            }
+            if (__builtin_expect(!ok, 0)) {
+                // some quotient left the fast path's exponent range (an exact zero, a denormal...):
+                // redo this thread's batch from the stored cells with the fully guarded division
+#pragma unroll
+                for (int u = 0; u < FUP_UNROLL; ++u)
+                    if (ii + u < rows) t[u] = ld_stream(srcp + (int64_t)(ii + u) * ld);
+                for (int l = 0; l < f; ++l) {
+                    const double2 rj = *reinterpret_cast<const double2 *>(&sm.rows[l][2 * tid]);
+                    const PivotDiv d = s_lvl[l].d;
+#pragma unroll
+                    for (int u = 0; u < FUP_UNROLL; ++u) {
+                        const double ci = sm.cols[l][ii + u];
+                        t[u].x = cell_update(t[u].x, d, rj.x, ci);
+                        t[u].y = cell_update(t[u].y, d, rj.y, ci);
+                    }
                 }
             }
         } else {
@@ -303,22 +527,29 @@ update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cb
 namespace spx_launch {
 
 int64_t colbuf_doubles(int n);
+int sm_count();
 
 int fuse_max() { return FUSE_MAX; }
 
 static inline int64_t align128(int64_t v) { return (v + 127) / 128 * 128; }
 
-// workspace: plan header | ROWS[FUSE_MAX][ld] | COLS[FUSE_MAX][cbd] | frow[ld] | bvec[n]
+// workspace: plan header | ROWS[FUSE_MAX][ld] | COLS[FUSE_MAX][cbd] | frow[ld] | bvec[n] | bvec2[n] |
+//            CoopScratch | ratio partials [FUSE_MAX][COOP_MAX_CTAS]
+constexpr int COOP_MAX_CTAS = 160;
+
 int64_t fused_workspace_bytes(int n, int64_t ld) {
     const int64_t cbd = colbuf_doubles(n);
     return align128(sizeof(PlanHeader)) + align128(FUSE_MAX * ld * 8) + align128(FUSE_MAX * cbd * 8) +
-           align128(ld * 8) + align128(((int64_t)n + 16) * 8);
+           align128(ld * 8) + 2 * align128(((int64_t)n + 16) * 8) + align128(sizeof(CoopScratch)) +
+           align128((int64_t)FUSE_MAX * COOP_MAX_CTAS * sizeof(Ratio));
 }
+
+static int g_coop_ctas = -1;      // co-resident CTAs of coop_price_kernel (0: cooperative launch unavailable)
 
 // one pass: price up to F pivots from the materialised table, then stream the body once
 cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, int m, int64_t ld, int rule,
-                       int F, spx_state *st, void *work, int32_t *rowlab, int32_t *collab, int32_t *trace,
-                       cudaStream_t stream) {
+                       int F, int minb, int pricing, spx_state *st, void *work, int32_t *rowlab, int32_t *collab,
+                       int32_t *trace, cudaStream_t stream) {
     if (F < 1) F = 1;
     if (F > FUSE_MAX) F = FUSE_MAX;
     const int64_t cbd = colbuf_doubles(n);
@@ -327,24 +558,52 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
     double *ROWS = reinterpret_cast<double *>(p);               p += align128(FUSE_MAX * ld * 8);
     double *COLS = reinterpret_cast<double *>(p);               p += align128(FUSE_MAX * cbd * 8);
     double *frow = reinterpret_cast<double *>(p);               p += align128(ld * 8);
-    double *bvec = reinterpret_cast<double *>(p);
-    PriceArgs a;
+    double *bvec = reinterpret_cast<double *>(p);               p += align128(((int64_t)n + 16) * 8);
+    double *bvec2 = reinterpret_cast<double *>(p);              p += align128(((int64_t)n + 16) * 8);
+    CoopScratch *cs = reinterpret_cast<CoopScratch *>(p);       p += align128(sizeof(CoopScratch));
+    Ratio *part = reinterpret_cast<Ratio *>(p);
+    CoopArgs ca;
+    PriceArgs &a = ca.a;
     a.A[0] = A0; a.A[1] = A1; a.b[0] = b0; a.b[1] = b1;
     a.n = n; a.m = m; a.ld = ld; a.cbd = cbd; a.rule = rule; a.F = F;
     a.st = st; a.plan = plan; a.ROWS = ROWS; a.COLS = COLS; a.frow = frow; a.bvec = bvec;
     a.rowlab = rowlab; a.collab = collab; a.trace = trace;
-    block_price_kernel<<<1, PRICE_THREADS, 0, stream>>>(a);
-    cudaError_t e = cudaGetLastError();
+    ca.bv[0] = bvec; ca.bv[1] = bvec2; ca.cs = cs; ca.part = part;
+    if (g_coop_ctas < 0) {
+        int dev = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        g_coop_ctas = 0;
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_price_kernel, 256, 0) == cudaSuccess &&
+            per_sm > 0)
+            g_coop_ctas = min(COOP_MAX_CTAS, sm_count());
+    }
+    cudaError_t e;
+    // pricing: 0 auto (whole-GPU cooperative kernel when the vectors are long enough), 1 one CTA, 2 cooperative
+    const bool coop = (pricing == 2 || (pricing == 0 && max(n, m) >= 4096)) && g_coop_ctas > 0;
+    if (coop) {
+        int G = (max(n + 1, (int)ld) + 255) / 256;
+        G = G > g_coop_ctas ? g_coop_ctas : (G < 1 ? 1 : G);
+        void *args[] = {&ca};
+        e = cudaLaunchCooperativeKernel((const void *)coop_price_kernel, dim3(G), dim3(256), args, 0, stream);
+    } else {
+        block_price_kernel<<<1, PRICE_THREADS, 0, stream>>>(a);
+        e = cudaGetLastError();
+    }
     if (e != cudaSuccess) return e;
     static bool configured = false;
     if (!configured) {
-        e = cudaFuncSetAttribute(update_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(FusedSmem));
-        if (e != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(update_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(update_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(update_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
         configured = true;
     }
     dim3 grid((unsigned)((m + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + FUP_TR - 1) / FUP_TR));
-    update_fused_kernel<2><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS);
+    switch (minb) {
+    case 2: update_fused_kernel<2><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
+    case 4: update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
+    default: update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
+    }
     spx_host::count_launch(2);
     return cudaGetLastError();
 }

@@ -411,7 +411,7 @@ int64_t colbuf_doubles(int n) {
     return ((int64_t)n + 1 + UPD_TR_MAX - 1) / UPD_TR_MAX * UPD_TR_MAX + UPD_TR_MAX;
 }
 
-int64_t g_opt[8] = {0, 0, 4, 0, 0, 0, 0, 0};
+int64_t g_opt[16] = {0, 0, 4, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 // Rows per tile.  Measured on B200 (tools/upd_lab.py, profiles/r1c_update_variants.md): the smallest
 // tile — 8 rows = exactly one 8-deep load batch per thread, 4 CTAs (64 registers) per SM — is the
@@ -425,7 +425,7 @@ static int pick_tr(int n, int m_loc) {
 
 // process-wide tuning knobs (spx_set_option); every setting computes the same bits
 
-int64_t get_option(int key) { return (key >= 0 && key < 8) ? g_opt[key] : -1; }
+int64_t get_option(int key) { return (key >= 0 && key < 16) ? g_opt[key] : -1; }
 int set_option(int key, int64_t value) {
     switch (key) {
     case SPX_OPT_UPDATE_KERNEL:    if (value < 0 || value > 2) return -1; break;
@@ -434,6 +434,8 @@ int set_option(int key, int64_t value) {
     case SPX_OPT_PIPE_GRID:        if (value < 0 || value > 4096) return -1; break;
     case SPX_OPT_TILED_ROWS:       if (value < 0 || value > UPD_TR_MAX || value % 8) return -1; break;
     case SPX_OPT_FUSE_DEPTH:       if (value < 0 || value > 8) return -1; break;
+    case SPX_OPT_FUSE_MIN_BLOCKS:  if (value < 0 || value > 4) return -1; break;
+    case SPX_OPT_FUSE_PRICING:     if (value < 0 || value > 2) return -1; break;
     default: return -1;
     }
     g_opt[key] = value;

@@ -14,6 +14,26 @@ from util import END_TO_STATUS, bits, case_inputs, flat_of, label_codes, table_s
 pytestmark = pytest.mark.gpu
 
 
+class loop_mode:
+    """'fused-coop' = the fused loop with the whole-GPU cooperative pricing kernel forced on (small
+    tableaus would pick the one-CTA pricing kernel); every other name passes through."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if self.name == "fused-coop":
+            from simplex_method_solver_b200 import _native as N
+            assert N.lib().spx_set_option(8, 2) == 0
+            return "fused"
+        return self.name
+
+    def __exit__(self, *a):
+        if self.name == "fused-coop":
+            from simplex_method_solver_b200 import _native as N
+            N.lib().spx_set_option(8, 0)
+
+
 @pytest.fixture(scope="module")
 def spx():
     import torch
@@ -100,7 +120,7 @@ def test_problem_files_feed_the_batched_solver(spx):
 
 # --------------------------------------------------------------------------- all golden cases
 @pytest.mark.parametrize("lookahead,chunk", [(False, 7), (True, 7), (True, 4), (True, 1), ("resident", 7), (None, 5),
-                                             ("fused", 7), ("fused", 3)])
+                                             ("fused", 7), ("fused", 3), ("fused-coop", 7)])
 def test_all_reference_cases_streaming_solver(spx, ref_cases, lookahead, chunk):
     """solve(): device-side loop, classic (pick k, update k, ...) and look-ahead (pivot k+1 priced
     from table k on a side stream while update k runs); trace, ending, labels, final table bits."""
@@ -108,7 +128,8 @@ def test_all_reference_cases_streaming_solver(spx, ref_cases, lookahead, chunk):
         rows, c = case_inputs(case)
         n, m = rows.shape[0], rows.shape[1] - 1
         sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
-        sol = sm.solve(max_pivots=case["cap"], chunk=chunk, lookahead=lookahead)
+        with loop_mode(lookahead) as mode_:
+            sol = sm.solve(max_pivots=case["cap"], chunk=chunk, lookahead=mode_)
         assert sol.status == END_TO_STATUS[case["end"]], case["name"]
         assert sol.trace.tolist() == case["trace"], case["name"]
         flat = sm._dev.export_flat(sm._npiv)
@@ -259,9 +280,14 @@ def test_pick_update_bit_exact_ragged_shapes(spx, n, m):
         assert dev.read_state().npiv == npiv
 
 
-@pytest.mark.parametrize("mode", ["resident", "fused"])
+@pytest.mark.parametrize("mode", ["resident", "fused", "fused-coop"])
 @pytest.mark.parametrize("n,m", [(1, 2), (3, 1), (7, 15), (9, 17), (64, 512), (65, 513), (130, 1030), (257, 100), (40, 2049)])
 def test_resident_and_fused_loops_bit_exact_ragged_shapes(spx, n, m, mode):
+    with loop_mode(mode) as mode_:
+        _ragged_loop(spx, n, m, mode_)
+
+
+def _ragged_loop(spx, n, m, mode):
     """The persistent L2-resident loop and the F-pivots-per-pass fused loop in steps of 1..9 pivots vs the
     oracle, whole table each time (odd step counts leave the table in either ping-pong buffer)."""
     rng = np.random.default_rng(n * 31 + m)
@@ -485,8 +511,13 @@ def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookah
 
 
 # --------------------------------------------------------------------------- BASELINE configs
-@pytest.mark.parametrize("lookahead", [False, True, "resident", "fused"])
+@pytest.mark.parametrize("lookahead", [False, True, "resident", "fused", "fused-coop"])
 def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests, lookahead):
+    with loop_mode(lookahead) as mode_:
+        _cfg2_full(spx, cfg_digests, mode_)
+
+
+def _cfg2_full(spx, cfg_digests, lookahead):
     g = cfg_digests["cfg2"]
     rows, c = W.dense_lp(1000, 2000, 0)
     assert W.input_digest(rows, c) == g["input_sha256"]

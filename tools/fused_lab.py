@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--m", type=int, default=32768)
     ap.add_argument("--pivots", type=int, default=400)
     ap.add_argument("--depths", default="1,2,4,8")
+    ap.add_argument("--minb", default="3")
     a = ap.parse_args()
     L = N.lib()
     rows, c = W.dense_lp(a.n, a.m, 0)
@@ -31,9 +32,11 @@ def main():
             gold = np.asarray(json.load(fh)["cfg4"]["trace"], dtype=np.int32)
     cells = a.n * (a.m + 1) + a.m
     tab = DeviceTableau(a.n, a.m, trace_capacity=4 * a.pivots + 64)
-    for mode, F in [("lookahead", 0)] + [("fused", int(x)) for x in a.depths.split(",")]:
+    for mode, F, mb in [("lookahead", 0, 0)] + [("fused", int(x), int(y)) for y in a.minb.split(",")
+                                                 for x in a.depths.split(",")]:
         if F:
             assert L.spx_set_option(N.OPT_FUSE_DEPTH, F) == 0
+            assert L.spx_set_option(7, mb) == 0
         tab.load(rows, c, max_pivots=4 * a.pivots + 32)
         tab.solve(stop_after=a.pivots, chunk=a.pivots, lookahead=mode)          # warm-up
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -47,7 +50,7 @@ def main():
             tr = tab.trace[:npiv].cpu().numpy()
             k = min(len(gold), npiv)
             ok = f" golden[{k}]={'OK' if (tr[:k] == gold[:k]).all() else 'MISMATCH'}"
-        print(f"{mode:9s} F={F}: {a.pivots} pivots in {ms:8.2f} ms  {a.pivots / ms * 1e3:8.1f} pivots/s  "
+        print(f"{mode:9s} F={F} minb={mb}: {a.pivots} pivots in {ms:8.2f} ms  {a.pivots / ms * 1e3:8.1f} pivots/s  "
               f"{ms / a.pivots * 1e3:7.1f} us/pivot  north-star {16.0 * cells * a.pivots / ms / 1e6:8.0f} GB/s  "
               f"status={st} npiv={npiv}{ok}", flush=True)
 
