@@ -98,7 +98,7 @@ int64_t     spx_launch_count(int reset);
 #define SPX_OPT_TILED_ROWS       5  /* tiled kernel rows per tile (0 = auto; else a multiple of 8 <= 64) */
 #define SPX_OPT_FUSE_PRICING     8  /* fused loop pricing kernel: 0 auto, 1 one CTA, 2 whole-GPU cooperative */
 #define SPX_OPT_FUSE_MIN_BLOCKS  7  /* fused update kernel: resident CTAs per SM its register budget targets (2..4, 0 = default) */
-#define SPX_OPT_FUSE_DEPTH       6  /* fused loop: pivots applied per pass over the body (0 = default 4, max 8) */
+#define SPX_OPT_FUSE_DEPTH       6  /* fused loop: pivots applied per pass over the body (0 = default 8, max 8) */
 int         spx_set_option(int32_t option, int64_t value);
 int64_t     spx_get_option(int32_t option);
 /* Device self-test of the hoisted-reciprocal division used by K3 against the
@@ -163,7 +163,7 @@ int spx_update(const double *d_Ain, double *d_Aout, const double *d_bin, double 
  * phase-1 row and the next entering column are O(n+m) cells computed with the update's own
  * arithmetic — so the update kernels run back to back and pricing is off the critical path.
  * Pivot sequence and every cell are identical in both modes. */
-#define SPX_LOOP_AUTO      0  /* resident if the tableau fits L2, look-ahead if >= 256 MB and a workspace is given, else classic */
+#define SPX_LOOP_AUTO      0  /* resident if the tableau fits L2; fused (else look-ahead) if >= 256 MB and the workspace allows; else classic */
 #define SPX_LOOP_CLASSIC   1
 #define SPX_LOOP_LOOKAHEAD 2
 #define SPX_LOOP_RESIDENT  3  /* ONE persistent cooperative kernel runs the whole loop (n <= 4095, both bodies in L2):
@@ -174,6 +174,13 @@ int spx_update(const double *d_Ain, double *d_Aout, const double *d_bin, double 
                                * Workspace: spx_fused_workspace_bytes(n, m).  Same pivots, same bits. */
 int64_t spx_solve_workspace_bytes(int32_t n);
 int64_t spx_fused_workspace_bytes(int32_t n, int32_t m);
+/* One pass of the fused loop on its own: phase 0 = price `depth` pivots + stream the body once,
+ * 1 = the pricing kernel only, 2 = the fused update kernel only (after a phase-1 call).  The index
+ * of the buffer holding the current table travels in d_state->reserved[0] (0/1); the caller sets it
+ * before the first pass.  Used by bench.py to time the two kernels separately. */
+int spx_fused_pass(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n, int32_t m, int64_t ld,
+                   int32_t rule, int32_t depth, int32_t phase, spx_state *d_state, void *d_work,
+                   int64_t work_bytes, int32_t *d_rowlab, int32_t *d_collab, int32_t *d_trace, void *stream);
 int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1,
               int32_t n, int32_t m, int64_t ld, int32_t rule,
               spx_state *d_state, double *d_colbuf, int32_t *d_rowlab, int32_t *d_collab,

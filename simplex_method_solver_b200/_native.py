@@ -72,6 +72,8 @@ SIGNATURES = {
     "spx_update": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spx_solve_workspace_bytes": (_i64, [_i32]),
     "spx_fused_workspace_bytes": (_i64, [_i32, _i32]),
+    "spx_fused_pass": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp,
+                                      _vp, _vp]),
     "spx_solve": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp,
                                  _i32, _i64, _i32, _vp, _i64, _pi32, _pi64, _vp]),
     "spx_extract": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -33,7 +33,7 @@ cudaError_t resident_loop(double *, double *, double *, double *, int, int, int6
                           double *, int32_t *, int32_t *, int32_t *, cudaStream_t);
 int fuse_max();
 int64_t fused_workspace_bytes(int, int64_t);
-cudaError_t fused_pass(double *, double *, double *, double *, int, int, int64_t, int, int, int, int, spx_state *,
+cudaError_t fused_pass(double *, double *, double *, double *, int, int, int64_t, int, int, int, int, int, spx_state *,
                        void *, int32_t *, int32_t *, int32_t *, cudaStream_t);
 int64_t get_option(int);
 int     set_option(int, int64_t);
@@ -312,6 +312,9 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
     if (mode == SPX_LOOP_AUTO) {
         // L2-resident tableaus: one persistent kernel; big ones: look-ahead streaming; else classic
         if (spx_launch::resident_fits(n, m, ld)) mode = SPX_LOOP_RESIDENT;
+        else if (d_work != nullptr && ((uintptr_t)d_work & 127) == 0 &&
+                 work_bytes >= spx_launch::fused_workspace_bytes(n, ld) &&
+                 (int64_t)(n + 1) * ld * 8 >= (256LL << 20)) mode = SPX_LOOP_FUSED;
         else if (d_work != nullptr && (int64_t)(n + 1) * ld * 8 >= (256LL << 20)) mode = SPX_LOOP_LOOKAHEAD;
         else mode = SPX_LOOP_CLASSIC;
     }
@@ -361,14 +364,14 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
             // passes of F pivots: price F levels from the stored table (one CTA, O((n+m)F^2) work), then
             // ONE stream over the body applies them all — 16 B of HBM traffic per cell per F pivots
             int F = (int)spx_launch::get_option(SPX_OPT_FUSE_DEPTH);
-            if (F <= 0) F = 4;
+            if (F <= 0) F = 8;
             if (F > spx_launch::fuse_max()) F = spx_launch::fuse_max();
             int64_t left = k;
             while (left > 0) {
                 const int Fp = (int)(left < F ? left : F);
                 if (check(spx_launch::fused_pass(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, Fp,
                                                  (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS),
-                                                 (int)spx_launch::get_option(SPX_OPT_FUSE_PRICING), d_state, d_work, d_rowlab,
+                                                 (int)spx_launch::get_option(SPX_OPT_FUSE_PRICING), 0, d_state, d_work, d_rowlab,
                                                  d_collab, d_trace, s), "fused pass launch")) return -1;
                 left -= Fp;
             }
@@ -442,6 +445,21 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
     if (h_status) *h_status = hs.status;
     if (h_npiv) *h_npiv = hs.npiv;
     return 0;
+}
+
+// one fused pass, or one of its two kernels (bench.py times them separately)
+int spx_fused_pass(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n, int32_t m, int64_t ld,
+                   int32_t rule, int32_t depth, int32_t phase, spx_state *d_state, void *d_work, int64_t work_bytes,
+                   int32_t *d_rowlab, int32_t *d_collab, int32_t *d_trace, void *stream) {
+    if (validate_split("spx_fused_pass", d_A0, d_b0, n, m, ld)) return -2;
+    if (validate_split("spx_fused_pass", d_A1, d_b1, n, m, ld)) return -2;
+    SPX_REQUIRE(d_state && d_work && d_rowlab && d_collab && ((uintptr_t)d_work & 127) == 0 &&
+                work_bytes >= spx_launch::fused_workspace_bytes(n, ld) && depth >= 1 && depth <= spx_launch::fuse_max() &&
+                phase >= 0 && phase <= 2, "spx_fused_pass: bad arguments");
+    return check(spx_launch::fused_pass(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, depth,
+                                        (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS),
+                                        (int)spx_launch::get_option(SPX_OPT_FUSE_PRICING), phase, d_state, d_work,
+                                        d_rowlab, d_collab, d_trace, as_stream(stream)), "fused pass launch");
 }
 
 // ---- find_optimum / f -----------------------------------------------------------

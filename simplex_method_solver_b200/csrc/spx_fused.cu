@@ -548,8 +548,8 @@ static int g_coop_ctas = -1;      // co-resident CTAs of coop_price_kernel (0: c
 
 // one pass: price up to F pivots from the materialised table, then stream the body once
 cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, int m, int64_t ld, int rule,
-                       int F, int minb, int pricing, spx_state *st, void *work, int32_t *rowlab, int32_t *collab,
-                       int32_t *trace, cudaStream_t stream) {
+                       int F, int minb, int pricing, int phase, spx_state *st, void *work, int32_t *rowlab,
+                       int32_t *collab, int32_t *trace, cudaStream_t stream) {
     if (F < 1) F = 1;
     if (F > FUSE_MAX) F = FUSE_MAX;
     const int64_t cbd = colbuf_doubles(n);
@@ -578,10 +578,13 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
             per_sm > 0)
             g_coop_ctas = min(COOP_MAX_CTAS, sm_count());
     }
-    cudaError_t e;
+    cudaError_t e = cudaSuccess;
+    // phase: 0 price + update, 1 price only, 2 update only (bench.py times the two kernels separately)
     // pricing: 0 auto (whole-GPU cooperative kernel when the vectors are long enough), 1 one CTA, 2 cooperative
     const bool coop = (pricing == 2 || (pricing == 0 && max(n, m) >= 4096)) && g_coop_ctas > 0;
-    if (coop) {
+    if (phase == 2) {
+        // nothing to price
+    } else if (coop) {
         int G = (max(n + 1, (int)ld) + 255) / 256;
         G = G > g_coop_ctas ? g_coop_ctas : (G < 1 ? 1 : G);
         void *args[] = {&ca};
@@ -591,6 +594,8 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e;
+    if (phase != 2) spx_host::count_launch();
+    if (phase == 1) return cudaSuccess;
     static bool configured = false;
     if (!configured) {
         if ((e = cudaFuncSetAttribute(update_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
@@ -601,10 +606,10 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
     dim3 grid((unsigned)((m + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + FUP_TR - 1) / FUP_TR));
     switch (minb) {
     case 2: update_fused_kernel<2><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
-    case 4: update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
-    default: update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
+    case 3: update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
+    default: update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
     }
-    spx_host::count_launch(2);
+    spx_host::count_launch();
     return cudaGetLastError();
 }
 

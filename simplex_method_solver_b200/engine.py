@@ -155,6 +155,14 @@ class DeviceTableau:
                    self.work.numel() * 8, ctypes.byref(st), ctypes.byref(npiv), self._stream())
         return st.value, npiv.value
 
+    def fused_pass(self, depth: int, phase: int = 0, rule: int = N.RULE_REFERENCE):
+        """One pass of the fused loop (phase 0), or its pricing (1) / streaming-update (2) kernel alone.
+        The caller keeps state.reserved[0] = index of the buffer holding the current table."""
+        self._call("spx_fused_pass", self.A[0].data_ptr(), self.A[1].data_ptr(), self.b[0].data_ptr(),
+                   self.b[1].data_ptr(), self.n, self.m, self.ld, rule, int(depth), int(phase),
+                   self.state.data_ptr(), self.work.data_ptr(), self.work.numel() * 8, self.rowlab.data_ptr(),
+                   self.collab.data_ptr(), N.ptr(self.trace))
+
     # -- results ----------------------------------------------------------------------
     def export_flat(self, npiv: int, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Current table -> host reference-flat array (what .table / Info.table expose)."""
