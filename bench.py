@@ -175,9 +175,10 @@ def config_dict(ngpu):
             "n": N_ROWS, "m": M_COLS, "cells": cells(N_ROWS, M_COLS),
             "pivots_per_step": PIVOTS_PER_STEP,
             "loop": "fused: 8 pivots priced from the stored table, then ONE stream over the body applies them (csrc/spx_fused.cu)"
-            if ngpu == 1 else "look-ahead: pivot k+1 priced during update k",
+            if ngpu == 1 else "fused, column-sharded: cooperative pricing with the in-kernel NVLink exchange of keys and "
+            "the pivot column, then one stream over the local columns per 8 pivots",
             "parallelism": "single GPU" if ngpu == 1 else
-            f"column-sharded x{ngpu}, look-ahead pricing, one candidate exchange per pivot (NVLink peer stores)",
+            f"column-sharded x{ngpu}, one key + one pivot-column exchange per pivot over NVLink peer memory",
             "l2_policy": "inputs (8.6 GB per pivot) far exceed the 126 MB L2; no flush needed",
             "rule": "reference (first-negative entering, max-negative-ratio leaving)"}
 
@@ -486,8 +487,12 @@ def run_ours(args):
         return
 
     # ---------------- N > 1: column-sharded, one process per GPU ---------------------------
-    from simplex_method_solver_b200.parallel import PeerShardedTableau, ShardedTableau
-    if args.exchange == "p2p":
+    from simplex_method_solver_b200.parallel import FusedShardedTableau, PeerShardedTableau, ShardedTableau
+    if args.exchange == "fused":
+        # passes of 8 pivots: cooperative pricing with the in-kernel NVLink exchange, then ONE stream
+        # over the local columns applies them all (csrc/spx_fused.cu)
+        sh = FusedShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
+    elif args.exchange == "p2p":
         # C-side look-ahead loop, candidates exchanged by NVLink peer stores (csrc/spx_shard.cu)
         sh = PeerShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
     else:
@@ -521,7 +526,7 @@ def run_ours(args):
     assert (tr[:k] == gold[:k]).all(), "sharded pivot sequence differs from the golden prefix"
     value = args.steps * P / (total_ms * 1e-3)
     alg_bytes = 16.0 * cells(N_ROWS, M_COLS)
-    if args.exchange == "p2p":
+    if args.exchange in ("p2p", "fused"):
         sh.close()
     del sh
     torch.cuda.empty_cache()
@@ -554,8 +559,9 @@ def main():
     ap.add_argument("--ref-pivots-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the cfg3 batched-LP leg")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N>1: candidate exchange by NVLink peer stores from the C loop (default) or NCCL all-gather")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "p2p", "nccl"],
+                    help="N>1: fused passes with the in-kernel NVLink exchange (default); pivot-at-a-time look-ahead "
+                         "with NVLink peer mailboxes (p2p) or an NCCL all-gather (nccl)")
     ap.add_argument("--no-lookahead", action="store_true",
                     help="classic pick->update order instead of pricing pivot k+1 during update k")
     args = ap.parse_args()

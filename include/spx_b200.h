@@ -293,6 +293,25 @@ int spx_shard_enqueue(spx_shard *h, int64_t pivots, void *stream);
 int spx_shard_read(spx_shard *h, spx_state *h_state, int32_t *cur_buffer, void *stream);
 int spx_shard_close(spx_shard *h);
 
+/* ---- the column-sharded FUSED loop (one process per GPU, csrc/spx_fused.cu) -------------------
+ * Passes of `depth` pivots: a whole-GPU cooperative kernel on every rank prices the next pivots by
+ * lazy replay and exchanges, per pivot and from INSIDE the kernel over NVLink peer memory, the
+ * ranks' 16-byte entering-column keys and the winning pivot column (stored by its owner straight
+ * into every rank's plane); then each rank streams its own columns once and applies all pivots.
+ * Each rank owns an XBOX (spx_fshard_xbox_bytes, zero-initialised, spx_device_alloc + CUDA IPC);
+ * `xboxes` lists every rank's XBOX as mapped into this process.  d_state->reserved[0] carries the
+ * index of the ping-pong buffer that holds the current table (0 after spx_init_state);
+ * spx_fshard_read returns it.  d_work: spx_fused_workspace_bytes(n, m_loc) bytes. */
+typedef struct spx_fshard spx_fshard;
+int64_t spx_fshard_xbox_bytes(int32_t n, int32_t nranks);
+int spx_fshard_open(spx_fshard **out, int32_t rank, int32_t nranks, int32_t n, int32_t m_loc, int64_t ld_loc,
+                    int64_t col0, int32_t rule, double *d_A0, double *d_A1, double *d_b0, double *d_b1,
+                    spx_state *d_state, void *d_work, int64_t work_bytes, int32_t *d_rowlab, int32_t *d_collab,
+                    int32_t *d_trace, void *const *xboxes);
+int spx_fshard_enqueue(spx_fshard *h, int64_t pivots, int32_t depth, void *stream);
+int spx_fshard_read(spx_fshard *h, spx_state *h_state, int32_t *cur_buffer, void *stream);
+int spx_fshard_close(spx_fshard *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,8 @@
 // (tests/test_gpu_parity.py runs this loop against the same goldens and the oracle).
 #include <cooperative_groups.h>
 
+#include <new>
+
 #include "spx_block.cuh"
 
 namespace cg = cooperative_groups;
@@ -412,6 +414,313 @@ coop_price_kernel(CoopArgs ca) {
     }
 }
 
+// ---- the cooperative pricing kernel for a COLUMN-SHARDED tableau (one process per GPU) ----------
+// Rank g owns the columns [col0, col0 + m) of the body; b, labels, state and the plan are replicated.
+// Per level the ranks exchange, straight from inside this kernel over NVLink peer memory:
+//   keys    every rank's best local entering column (16 B) -> every rank's XBOX key slots + flag;
+//   column  the OWNER of the winning column builds it (gather + replay) and its threads store the
+//           n+1 cells into every rank's COLS plane, then a flag; everyone else waits for the flag.
+// The ratio test, the b column and the level bookkeeping are computed redundantly (bit-identically)
+// on every rank.  XBOX of one rank:  COLS[2][FUSE_MAX][cbd] | keys[FUSE_MAX+1][2][R][2] |
+// kflag[FUSE_MAX+1][2][R] | cflag[2][FUSE_MAX]  — COLS is double-buffered by pass parity because a fast
+// rank may price pass q+1 while a slow rank's update kernel still reads the planes of pass q.
+constexpr int XB_MAX_RANKS = 16;
+
+struct XBoxLayout {
+    int64_t cols_off, keys_off, kflag_off, cflag_off, bytes;
+};
+__host__ __device__ inline XBoxLayout xbox_layout(int64_t cbd, int R) {
+    XBoxLayout L;
+    L.cols_off = 0;
+    L.keys_off = (2LL * FUSE_MAX * cbd * 8 + 127) / 128 * 128;
+    L.kflag_off = L.keys_off + ((int64_t)(FUSE_MAX + 1) * 2 * R * 16 + 127) / 128 * 128;
+    L.cflag_off = L.kflag_off + ((int64_t)(FUSE_MAX + 1) * 2 * R * 8 + 127) / 128 * 128;
+    L.bytes = L.cflag_off + (2LL * FUSE_MAX * 8 + 127) / 128 * 128;
+    return L;
+}
+
+struct ShardArgs {
+    CoopArgs ca;                 // a.m = local columns, a.ld = local leading dimension, a.ROWS local planes
+    int rank, R;
+    int64_t col0;
+    unsigned long long seq;      // pass number (1, 2, ...): the value the flags of this pass carry
+    unsigned char *xbox[XB_MAX_RANKS];   // every rank's XBOX mapped into this process ([rank] = local)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag >= seq; false after 20 s (a peer died)
+__device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigned long long seq) {
+    const unsigned long long t0 = gtimer_ns();
+    while (ld_acquire_sys(flag) < seq) {
+        if (gtimer_ns() - t0 > 20000000000ull) return false;
+        __nanosleep(64);
+    }
+    return true;
+}
+
+// CTA 0 only: publish this rank's key of (level, kind) to every rank, collect everyone's, pick the
+// lexicographic minimum.  Returns through sel[0] = global column (or SPX_NONE), sel[1] = owner rank,
+// sel[2] = 0 / 1 (timeout).
+__device__ void exchange_keys(const ShardArgs &sa, const XBoxLayout &XL, int level, int kind,
+                              unsigned long long kh, unsigned long long kl, int *sel) {
+    const int tid = threadIdx.x, R = sa.R;
+    __shared__ int s_to;
+    if (tid == 0) s_to = 0;
+    __syncthreads();
+    if (tid < R) {
+        unsigned char *box = sa.xbox[tid];
+        unsigned long long *slot = reinterpret_cast<unsigned long long *>(box + XL.keys_off) +
+                                   (((int64_t)level * 2 + kind) * R + sa.rank) * 2;
+        slot[0] = kh; slot[1] = kl;
+        unsigned long long *fl = reinterpret_cast<unsigned long long *>(box + XL.kflag_off) +
+                                 ((int64_t)level * 2 + kind) * R + sa.rank;
+        st_release_sys(fl, sa.seq);                      // release: the two key words are visible first
+        // ... and wait for rank `tid`'s key in MY box
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(sa.xbox[sa.rank] + XL.kflag_off) +
+                                         ((int64_t)level * 2 + kind) * R + tid;
+        if (!wait_seq(mine, sa.seq)) s_to = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long bh = ~0ull, bl = ~0ull; int win = -1;
+        const unsigned long long *keys = reinterpret_cast<const unsigned long long *>(sa.xbox[sa.rank] + XL.keys_off) +
+                                         ((int64_t)level * 2 + kind) * R * 2;
+        for (int g = 0; g < R; ++g) {
+            const unsigned long long h = __ldcg(keys + 2 * g), l = __ldcg(keys + 2 * g + 1);
+            if (l != ~0ull && (win < 0 || h < bh || (h == bh && l < bl))) { bh = h; bl = l; win = g; }
+        }
+        sel[0] = (win < 0) ? SPX_NONE : (int)bl;
+        sel[1] = win;
+        sel[2] = s_to;
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+shard_price_kernel(ShardArgs sa) {
+    cg::grid_group grid = cg::this_grid();
+    const CoopArgs &ca = sa.ca;
+    const PriceArgs &a = ca.a;
+    __shared__ Scratch s;
+    __shared__ LevelDiv s_lvl[FUSE_MAX];
+    __shared__ double s_scal[FUSE_MAX];
+    const int n = a.n, m = a.m, tid = threadIdx.x;
+    const int G = gridDim.x, gtid = blockIdx.x * blockDim.x + tid, gn = G * blockDim.x;
+    const int64_t ld = a.ld, cbd = a.cbd, col0 = sa.col0;
+    const XBoxLayout XL = xbox_layout(cbd, sa.R);
+    const int par = (int)(sa.seq & 1ull);
+    // this pass's COLS planes in MY box (every rank fills its own copy from the owners' stores)
+    double *COLS = reinterpret_cast<double *>(sa.xbox[sa.rank] + XL.cols_off) + (int64_t)par * FUSE_MAX * cbd;
+    int *gsel = &ca.cs->idx[FUSE_MAX][0];               // CTA 0 -> grid: {column, owner, timeout} of the last exchange
+
+    if (a.st->status != SPX_PIVOT) {                     // uniform over the grid AND over the ranks
+        if (gtid == 0) a.plan->f = 0;
+        return;
+    }
+    const int cur = (int)a.st->reserved[0] & 1;
+    const double *A = a.A[cur];
+    const int64_t npiv0 = a.st->npiv, cap = a.st->max_pivots;
+
+    if (blockIdx.x == 0)
+        for (int k = tid; k < (FUSE_MAX + 1) * 4; k += blockDim.x) {
+            ca.cs->idx[k / 4][k % 4] = SPX_NONE;
+            if (k % 4 == 0) ca.cs->key[k / 4] = ~0ull;
+        }
+    grid.sync();
+
+    int status = SPX_PIVOT, f = 0, last_r = -1, last_c = -1, phase1 = 0;
+    double last_p = 0.0;
+    for (int i = 0; i <= a.F; ++i) {
+        // ---------------- phase A (see coop_price_kernel): running b (replicated), local f row shard,
+        // local shard of ROW_{i-1}, first-negative folds
+        double *bout = ca.bv[i & 1];
+        int bneg = SPX_NONE, fneg = SPX_NONE;
+        unsigned long long fkey = ~0ull;
+        if (i == 0) {
+            for (int t = gtid; t < n; t += gn) { const double v = a.b[cur][t]; bout[t] = v; if (v < 0.0) bneg = min(bneg, t); }
+            for (int j = gtid; j < m; j += gn) {
+                const double v = A[(int64_t)n * ld + j];
+                a.frow[j] = v;
+                if (v < 0.0) { fneg = min(fneg, j); const unsigned long long k = orderable(v); fkey = k < fkey ? k : fkey; }
+            }
+        } else {
+            const LevelDiv L = s_lvl[i - 1];             // L.c is the LOCAL index of the pivot column or -1
+            const double *bin = ca.bv[(i - 1) & 1];
+            const double *COLL = COLS + (int64_t)(i - 1) * cbd;
+            const double br = __ldcg(bin + L.r), fc = __ldcg(COLL + n);
+            for (int t = gtid; t < n; t += gn) {
+                const double bt = __ldcg(bin + t);
+                const double v = (t == L.r) ? pivot_div(-bt, L.d) : cell_update(bt, L.d, br, __ldcg(COLL + t));
+                bout[t] = v;
+                if (v < 0.0) bneg = min(bneg, t);
+            }
+            if (tid < i - 1) s_scal[tid] = __ldcg(COLS + (int64_t)tid * cbd + L.r);
+            __syncthreads();
+            double *ROWL = a.ROWS + (int64_t)(i - 1) * ld;
+            const double *rowp = A + (int64_t)L.r * ld;
+            for (int j = gtid; j < ld; j += gn) {
+                if (j >= m) { ROWL[j] = 0.0; continue; }
+                double rv = rowp[j];
+                for (int l = 0; l < i - 1; ++l)
+                    rv = apply_level(rv, L.r, j, s_lvl[l], __ldcg(a.ROWS + (int64_t)l * ld + j), s_scal[l]);
+                ROWL[j] = rv;
+                const double fj = a.frow[j];
+                const double v = (j == L.c) ? pivot_div(fc, L.d) : cell_update(fj, L.d, rv, fc);
+                a.frow[j] = v;
+                if (v < 0.0) { fneg = min(fneg, j); const unsigned long long k = orderable(v); fkey = k < fkey ? k : fkey; }
+            }
+        }
+        if (i == a.F) { f = a.F; break; }
+        bneg = block_min_int(bneg, s);
+        fneg = block_min_int(fneg, s);
+        if (tid == 0) {
+            if (bneg != SPX_NONE) atomicMin(&ca.cs->idx[i][0], bneg);
+            if (fneg != SPX_NONE) atomicMin(&ca.cs->idx[i][1], fneg);
+        }
+        if (a.rule == SPX_RULE_DANTZIG) {
+            fkey = block_min_u64(fkey, s);
+            if (tid == 0 && fkey != ~0ull) atomicMin(&ca.cs->key[i], fkey);
+        }
+        grid.sync();
+        const int rb = __ldcg(&ca.cs->idx[i][0]);
+        const int r1 = (rb == SPX_NONE) ? -1 : rb;       // identical on every rank: b is replicated
+        int cloc = __ldcg(&ca.cs->idx[i][1]);            // this rank's candidate (local index)
+        unsigned long long kh = 0ull;
+        int kind = 0;
+        if (r1 >= 0) {
+            // phase-1: first positive cell of the local part of the virtual row r1 (:82-85)
+            kind = 1;
+            if (tid < i) s_scal[tid] = __ldcg(COLS + (int64_t)tid * cbd + r1);
+            __syncthreads();
+            const double *row = A + (int64_t)r1 * ld;
+            int loc = SPX_NONE;
+            for (int j = gtid; j < m; j += gn) {
+                double v = row[j];
+                for (int l = 0; l < i; ++l) v = apply_level(v, r1, j, s_lvl[l], __ldcg(a.ROWS + (int64_t)l * ld + j), s_scal[l]);
+                if (v > 0.0) { loc = j; break; }
+            }
+            loc = block_min_int(loc, s);
+            if (tid == 0 && loc != SPX_NONE) atomicMin(&ca.cs->idx[i][2], loc);
+            grid.sync();
+            cloc = __ldcg(&ca.cs->idx[i][2]);
+        } else if (a.rule == SPX_RULE_DANTZIG && cloc != SPX_NONE) {
+            const unsigned long long best = __ldcg(&ca.cs->key[i]);
+            int loc = SPX_NONE;
+            for (int j = gtid; j < m; j += gn) {
+                const double v = a.frow[j];
+                if (v < 0.0 && orderable(v) == best) { loc = j; break; }
+            }
+            loc = block_min_int(loc, s);
+            if (tid == 0 && loc != SPX_NONE) atomicMin(&ca.cs->idx[i][2], loc);
+            grid.sync();
+            cloc = __ldcg(&ca.cs->idx[i][2]);
+            kh = best;
+        }
+        // ---------------- exchange the keys, pick the global entering column and its owner
+        if (blockIdx.x == 0)
+            exchange_keys(sa, XL, i, kind, (cloc == SPX_NONE) ? ~0ull : kh,
+                          (cloc == SPX_NONE) ? ~0ull : (unsigned long long)(col0 + cloc), gsel);
+        grid.sync();
+        const int c = __ldcg(gsel + 0), owner = __ldcg(gsel + 1);
+        if (__ldcg(gsel + 2)) { status = SPX_PEER_TIMEOUT; f = i; break; }
+        if (c == SPX_NONE) { status = (r1 >= 0) ? SPX_INCORRECT : SPX_OPTIMAL; phase1 = (r1 >= 0); f = i; break; }
+        const int64_t cl64 = (int64_t)c - col0;
+        const int clocal = (cl64 >= 0 && cl64 < m) ? (int)cl64 : -1;
+
+        // ---------------- phase B: the owner builds the column and stores it into every rank's plane
+        if (owner == sa.rank) {
+            if (tid < i) s_scal[tid] = __ldcg(a.ROWS + (int64_t)tid * ld + clocal);
+            __syncthreads();
+            for (int t = gtid; t <= n; t += gn) {
+                double w = A[(int64_t)t * ld + clocal];
+                for (int l = 0; l < i; ++l) w = apply_level(w, t, clocal, s_lvl[l], s_scal[l], __ldcg(COLS + (int64_t)l * cbd + t));
+                for (int g = 0; g < sa.R; ++g)
+                    (reinterpret_cast<double *>(sa.xbox[g] + XL.cols_off) + ((int64_t)par * FUSE_MAX + i) * cbd)[t] = w;
+            }
+            __threadfence_system();
+            grid.sync();
+            if (blockIdx.x == 0 && tid < sa.R)
+                st_release_sys(reinterpret_cast<unsigned long long *>(sa.xbox[tid] + XL.cflag_off) + par * FUSE_MAX + i, sa.seq);
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+            const unsigned long long *fl = reinterpret_cast<const unsigned long long *>(sa.xbox[sa.rank] + XL.cflag_off) +
+                                           par * FUSE_MAX + i;
+            gsel[3] = wait_seq(fl, sa.seq) ? 0 : 1;
+        }
+        grid.sync();
+        if (__ldcg(gsel + 3)) { status = SPX_PEER_TIMEOUT; f = i; break; }
+
+        // ---------------- ratio fold on the received column (every rank, identical) (:107-136)
+        double *COLi = COLS + (int64_t)i * cbd;
+        Ratio q = ratio_identity();
+        if (r1 < 0)
+            for (int t = gtid; t < n; t += gn) ratio_accumulate(q, t, __ldcg(COLi + t), bout[t]);
+        q = block_ratio_reduce(q, s);
+        Ratio *part = ca.part + (int64_t)i * G;
+        if (tid == 0) part[blockIdx.x] = q;
+        grid.sync();
+        int r;
+        if (r1 >= 0) {
+            r = r1;
+        } else {
+            Ratio z = ratio_identity();
+            for (int k = tid; k < G; k += blockDim.x) {
+                Ratio y;
+                y.neg_val = __ldcg(&part[k].neg_val); y.neg_row = __ldcg(&part[k].neg_row);
+                y.zero_row = __ldcg(&part[k].zero_row); y.elig_row = __ldcg(&part[k].elig_row);
+                z = ratio_merge(z, y);
+            }
+            z = block_ratio_reduce(z, s);
+            bool elig_nan = false;
+            if (z.elig_row != SPX_NONE) {
+                const double v = __ddiv_rn(__ldcg(bout + z.elig_row), __ldcg(COLi + z.elig_row));
+                elig_nan = (v != v);
+            }
+            r = ratio_decide(z, elig_nan);
+            if (r < 0) { status = SPX_NOCONV; f = i; break; }
+        }
+        const double p = __ldcg(COLi + r);
+        if (npiv0 + i >= cap) { status = SPX_CAP; last_r = r; last_c = c; last_p = p; f = i; break; }
+        __syncthreads();
+        if (tid == 0) {
+            s_lvl[i].r = r; s_lvl[i].c = clocal; s_lvl[i].d = pivot_div_prepare(p);
+            if (blockIdx.x == 0) {
+                a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p;       // GLOBAL column in the plan
+                const int32_t tmp = a.rowlab[c]; a.rowlab[c] = a.collab[r]; a.collab[r] = tmp;
+                if (a.trace) { a.trace[2 * (npiv0 + i)] = r; a.trace[2 * (npiv0 + i) + 1] = c; }
+            }
+        }
+        __syncthreads();
+        last_r = r; last_c = c; last_p = p; phase1 = (r1 >= 0);
+    }
+
+    if (f > 0) {
+        grid.sync();
+        const double *bfin = ca.bv[f & 1];
+        for (int t = gtid; t < n; t += gn) a.b[cur ^ 1][t] = __ldcg(bfin + t);
+    }
+    if (gtid == 0) {
+        a.plan->f = f;
+        a.plan->src = cur;
+        spx_state *st = a.st;
+        st->status = status; st->r = last_r; st->c = last_c; st->p = last_p;
+        st->npiv = npiv0 + f; st->phase1 = phase1; st->slot = 0;
+        st->hint_tag[0] = st->hint_tag[1] = -1;
+        st->reserved[0] = (f > 0) ? (cur ^ 1) : cur;
+    }
+}
+
 // ---- the fused streaming update: one pass over the body applies plan->f levels -----------------
 struct FusedSmem {
     double rows[FUSE_MAX][FUP_TC];      // per level: slice of ROW_l for this column tile
@@ -420,7 +729,7 @@ struct FusedSmem {
 
 template <int MINB>
 __global__ void __launch_bounds__(FUP_THREADS, MINB)
-update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd,
+update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0,
                     const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
                     const double *__restrict__ COLS) {
     const int f = plan->f;
@@ -451,7 +760,9 @@ update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cb
     }
     if (tid < f) {
         s_lvl[tid].r = plan->lvl[tid].r;
-        s_lvl[tid].c = plan->lvl[tid].c;
+        // the plan carries GLOBAL column indices; this shard owns [col0, col0 + m)
+        const int64_t cl = (int64_t)plan->lvl[tid].c - col0;
+        s_lvl[tid].c = (cl >= 0 && cl < m) ? (int)cl : -1;
         s_lvl[tid].d = pivot_div_prepare(plan->lvl[tid].p);
     }
     __syncthreads();
@@ -578,6 +889,7 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
             per_sm > 0)
             g_coop_ctas = min(COOP_MAX_CTAS, sm_count());
     }
+    const int64_t col0 = 0;
     cudaError_t e = cudaSuccess;
     // phase: 0 price + update, 1 price only, 2 update only (bench.py times the two kernels separately)
     // pricing: 0 auto (whole-GPU cooperative kernel when the vectors are long enough), 1 one CTA, 2 cooperative
@@ -605,12 +917,160 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
     }
     dim3 grid((unsigned)((m + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + FUP_TR - 1) / FUP_TR));
     switch (minb) {
-    case 2: update_fused_kernel<2><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
-    case 3: update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
-    default: update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, plan, ROWS, COLS); break;
+    case 2: update_fused_kernel<2><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, col0, plan, ROWS, COLS); break;
+    case 3: update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, col0, plan, ROWS, COLS); break;
+    default: update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, col0, plan, ROWS, COLS); break;
     }
     spx_host::count_launch();
     return cudaGetLastError();
 }
 
+static int g_shard_ctas = -1;
+
+// one pass of the column-sharded fused loop on this rank: cooperative pricing with the in-kernel
+// NVLink exchange, then the fused update of the local columns
+cudaError_t fused_shard_pass(double *A0, double *A1, double *b0, double *b1, int n, int m_loc, int64_t ld, int64_t col0,
+                             int rule, int F, int minb, spx_state *st, void *work, int32_t *rowlab, int32_t *collab,
+                             int32_t *trace, int rank, int R, unsigned long long seq, void *const *xboxes,
+                             cudaStream_t stream) {
+    if (F < 1) F = 1;
+    if (F > FUSE_MAX) F = FUSE_MAX;
+    const int64_t cbd = colbuf_doubles(n);
+    char *p = static_cast<char *>(work);
+    PlanHeader *plan = reinterpret_cast<PlanHeader *>(p);       p += align128(sizeof(PlanHeader));
+    double *ROWS = reinterpret_cast<double *>(p);               p += align128(FUSE_MAX * ld * 8);
+    p += align128(FUSE_MAX * cbd * 8);                          // (the COLS planes live in the XBOX instead)
+    double *frow = reinterpret_cast<double *>(p);               p += align128(ld * 8);
+    double *bvec = reinterpret_cast<double *>(p);               p += align128(((int64_t)n + 16) * 8);
+    double *bvec2 = reinterpret_cast<double *>(p);              p += align128(((int64_t)n + 16) * 8);
+    CoopScratch *cs = reinterpret_cast<CoopScratch *>(p);       p += align128(sizeof(CoopScratch));
+    Ratio *part = reinterpret_cast<Ratio *>(p);
+    ShardArgs sa;
+    PriceArgs &a = sa.ca.a;
+    a.A[0] = A0; a.A[1] = A1; a.b[0] = b0; a.b[1] = b1;
+    a.n = n; a.m = m_loc; a.ld = ld; a.cbd = cbd; a.rule = rule; a.F = F;
+    a.st = st; a.plan = plan; a.ROWS = ROWS; a.COLS = nullptr; a.frow = frow; a.bvec = bvec;
+    a.rowlab = rowlab; a.collab = collab; a.trace = trace;
+    sa.ca.bv[0] = bvec; sa.ca.bv[1] = bvec2; sa.ca.cs = cs; sa.ca.part = part;
+    sa.rank = rank; sa.R = R; sa.col0 = col0; sa.seq = seq;
+    for (int g = 0; g < XB_MAX_RANKS; ++g) sa.xbox[g] = g < R ? static_cast<unsigned char *>(xboxes[g]) : nullptr;
+    if (g_shard_ctas < 0) {
+        int dev = 0, coop = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        g_shard_ctas = 0;
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shard_price_kernel, 256, 0) == cudaSuccess &&
+            per_sm > 0)
+            g_shard_ctas = min(COOP_MAX_CTAS, sm_count());
+    }
+    if (g_shard_ctas <= 0) return cudaErrorNotSupported;
+    int G = (max(n + 1, (int)ld) + 255) / 256;
+    G = G > g_shard_ctas ? g_shard_ctas : (G < 1 ? 1 : G);
+    void *args[] = {&sa};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)shard_price_kernel, dim3(G), dim3(256), args, 0, stream);
+    if (e != cudaSuccess) return e;
+    spx_host::count_launch();
+    static bool configured = false;
+    if (!configured) {
+        if ((e = cudaFuncSetAttribute(update_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(update_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
+        configured = true;
+    }
+    const XBoxLayout XL = xbox_layout(cbd, R);
+    const double *COLS = reinterpret_cast<const double *>(static_cast<unsigned char *>(xboxes[rank]) + XL.cols_off) +
+                         (int64_t)(seq & 1ull) * FUSE_MAX * cbd;
+    dim3 grid((unsigned)((m_loc + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + FUP_TR - 1) / FUP_TR));
+    if (grid.x == 0) return cudaSuccess;                     // a shard without columns only prices
+    if (minb == 3)
+        update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m_loc, ld, cbd, col0, plan, ROWS, COLS);
+    else
+        update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m_loc, ld, cbd, col0, plan, ROWS, COLS);
+    spx_host::count_launch();
+    return cudaGetLastError();
+}
+
+int64_t xbox_bytes(int n, int R) { return xbox_layout(colbuf_doubles(n), R).bytes; }
+int xbox_max_ranks() { return XB_MAX_RANKS; }
+
 } // namespace spx_launch
+
+// ---- C ABI of the column-sharded fused loop (declared in include/spx_b200.h) -------------------
+struct spx_fshard {
+    int rank, R, n, m_loc, rule;
+    int64_t ld, col0;
+    double *A[2], *b[2];
+    spx_state *st;
+    void *work;
+    int32_t *rowlab, *collab, *trace;
+    void *xbox[16];
+    unsigned long long seq;
+};
+
+extern "C" {
+
+int64_t spx_fshard_xbox_bytes(int32_t n, int32_t nranks) {
+    if (n < 1 || nranks < 1 || nranks > spx_launch::xbox_max_ranks()) return -1;
+    return spx_launch::xbox_bytes(n, nranks);
+}
+
+int spx_fshard_open(spx_fshard **out, int32_t rank, int32_t nranks, int32_t n, int32_t m_loc, int64_t ld_loc,
+                    int64_t col0, int32_t rule, double *d_A0, double *d_A1, double *d_b0, double *d_b1,
+                    spx_state *d_state, void *d_work, int64_t work_bytes, int32_t *d_rowlab, int32_t *d_collab,
+                    int32_t *d_trace, void *const *xboxes) {
+    using spx_host::set_error;
+    if (!out || !d_A0 || !d_A1 || !d_b0 || !d_b1 || !d_state || !d_work || !d_rowlab || !d_collab || !xboxes ||
+        nranks < 1 || nranks > spx_launch::xbox_max_ranks() || rank < 0 || rank >= nranks || n < 1 || m_loc < 0 ||
+        ld_loc < 16 || ld_loc % 16 || ld_loc < m_loc || col0 < 0 || ((uintptr_t)d_work & 127) ||
+        work_bytes < spx_launch::fused_workspace_bytes(n, ld_loc) ||
+        (rule != SPX_RULE_REFERENCE && rule != SPX_RULE_DANTZIG)) {
+        set_error("spx_fshard_open: bad arguments");
+        return -2;
+    }
+    spx_fshard *h = new (std::nothrow) spx_fshard();
+    if (!h) { set_error("spx_fshard_open: out of host memory"); return -2; }
+    h->rank = rank; h->R = nranks; h->n = n; h->m_loc = m_loc; h->rule = rule; h->ld = ld_loc; h->col0 = col0;
+    h->A[0] = d_A0; h->A[1] = d_A1; h->b[0] = d_b0; h->b[1] = d_b1;
+    h->st = d_state; h->work = d_work; h->rowlab = d_rowlab; h->collab = d_collab; h->trace = d_trace;
+    for (int g = 0; g < nranks; ++g) {
+        if (!xboxes[g]) { delete h; set_error("spx_fshard_open: null xbox %d", g); return -2; }
+        h->xbox[g] = xboxes[g];
+    }
+    h->seq = 0;
+    *out = h;
+    return 0;
+}
+
+// Enqueue `pivots` pivots as passes of `depth` (the last one shorter).  Every rank must make the
+// same call.  Asynchronous.
+int spx_fshard_enqueue(spx_fshard *h, int64_t pivots, int32_t depth, void *stream) {
+    if (!h || pivots < 0) { spx_host::set_error("spx_fshard_enqueue: bad arguments"); return -2; }
+    if (depth <= 0) depth = 8;
+    if (depth > spx_launch::fuse_max()) depth = spx_launch::fuse_max();
+    int64_t left = pivots;
+    while (left > 0) {
+        const int F = (int)(left < depth ? left : depth);
+        if (spx_host::check(spx_launch::fused_shard_pass(h->A[0], h->A[1], h->b[0], h->b[1], h->n, h->m_loc, h->ld, h->col0,
+                                                         h->rule, F, 0, h->st, h->work, h->rowlab, h->collab, h->trace,
+                                                         h->rank, h->R, ++h->seq, h->xbox,
+                                                         reinterpret_cast<cudaStream_t>(stream)), "fused shard pass"))
+            return -1;
+        left -= F;
+    }
+    return 0;
+}
+
+int spx_fshard_read(spx_fshard *h, spx_state *h_state, int32_t *cur_buffer, void *stream) {
+    if (!h || !h_state) { spx_host::set_error("spx_fshard_read: bad arguments"); return -2; }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (spx_host::check(cudaMemcpyAsync(h_state, h->st, sizeof(spx_state), cudaMemcpyDeviceToHost, s), "read state")) return -1;
+    if (spx_host::check(cudaStreamSynchronize(s), "sync")) return -1;
+    if (cur_buffer) *cur_buffer = (int32_t)(h_state->reserved[0] & 1);
+    return 0;
+}
+
+int spx_fshard_close(spx_fshard *h) {
+    delete h;
+    return 0;
+}
+
+} // extern "C"

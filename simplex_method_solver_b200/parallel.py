@@ -377,6 +377,128 @@ class ShardedTableau:
         return self.b[self.npiv_enqueued & 1, : self.n]
 
 
+class PeerRegion:
+    """`nbytes` of zeroed device memory on every rank, each rank's block mapped into every process
+    (cudaMalloc + CUDA IPC; handles exchanged once through torch.distributed)."""
+
+    def __init__(self, nbytes: int, rank: int, world: int, device, group=None):
+        L = N.lib()
+        self.rank, self.world, self.device, self.group = int(rank), int(world), torch.device(device), group
+        self._opened = []
+        with torch.cuda.device(self.device):
+            local = ctypes.c_void_p()
+            N.call("spx_device_alloc", ctypes.byref(local), int(nbytes))
+            self.local = int(local.value)
+            ptrs = [None] * self.world
+            ptrs[self.rank] = self.local
+            if self.world > 1:
+                hb = int(L.spx_ipc_handle_bytes())
+                buf = (ctypes.c_ubyte * hb)()
+                N.call("spx_ipc_export", self.local, buf)
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(buf), group=group)
+                for g in range(self.world):
+                    if g == self.rank:
+                        continue
+                    q = ctypes.c_void_p()
+                    N.call("spx_ipc_import", (ctypes.c_ubyte * hb).from_buffer_copy(handles[g]), ctypes.byref(q))
+                    ptrs[g] = int(q.value)
+                    self._opened.append(int(q.value))
+            self.ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for q in self._opened:
+                N.call("spx_ipc_close", q)
+            self._opened = []
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)           # nobody frees a block a peer still has mapped
+            if self.local:
+                N.call("spx_device_free", self.local)
+                self.local = 0
+
+
+class FusedShardedTableau(ShardedTableau):
+    """The column-sharded FUSED loop (csrc/spx_fused.cu, spx_fshard_*): passes of `depth` pivots —
+    a whole-GPU cooperative kernel per rank prices them by lazy replay, exchanging keys and the
+    winning pivot column from inside the kernel over NVLink peer memory, then every rank streams its
+    own columns ONCE for all of them.  Same pivots and bits as every other loop."""
+
+    def __init__(self, n: int, m: int, rank: int, world: int, device, trace_capacity: int = 0,
+                 group=None, rule: int = N.RULE_REFERENCE, depth: int = 8):
+        super().__init__(n, m, rank, world, device, trace_capacity=trace_capacity, group=group, rule=rule,
+                         lookahead=False)
+        L = N.lib()
+        self.depth = int(depth)
+        dev = self.device
+        wbytes = int(L.spx_fused_workspace_bytes(self.n, max(self.m_loc, 1)))
+        self.work = torch.zeros(wbytes // 8 + 16, dtype=torch.float64, device=dev)
+        self.xbox = PeerRegion(int(L.spx_fshard_xbox_bytes(self.n, world)), rank, world, dev, group=group)
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(dev):
+            N.call("spx_fshard_open", ctypes.byref(self.handle), rank, world, self.n, self.m_loc, self.ld, self.col0,
+                   rule, self.A[0].data_ptr(), self.A[1].data_ptr(), self.b[0].data_ptr(), self.b[1].data_ptr(),
+                   self.state.data_ptr(), self.work.data_ptr(), self.work.numel() * 8, self.rowlab.data_ptr(),
+                   self.collab.data_ptr(), N.ptr(self.trace), self.xbox.ptrs)
+        self._cur = 0
+
+    def load(self, rows, function, max_pivots: int):
+        super().load(rows, function, max_pivots)       # init_state leaves reserved[0] = 0: table 0 in buffer 0
+        self._cur = 0
+
+    def step(self):
+        self.run(1)
+
+    def run(self, pivots: int, check_every: int = 0):
+        done = 0
+        while done < pivots:
+            k = pivots - done if check_every <= 0 else min(check_every, pivots - done)
+            with torch.cuda.device(self.device):
+                N.call("spx_fshard_enqueue", self.handle, k, self.depth,
+                       torch.cuda.current_stream(self.device).cuda_stream)
+            done += k
+            if check_every > 0:
+                st = self.read_state()
+                if st.status != N.PIVOT:
+                    return st
+        return None
+
+    def read_state(self) -> N.SpxState:
+        st = N.SpxState()
+        cur = ctypes.c_int32(0)
+        with torch.cuda.device(self.device):
+            N.call("spx_fshard_read", self.handle, ctypes.byref(st), ctypes.byref(cur),
+                   torch.cuda.current_stream(self.device).cuda_stream)
+        self._cur = int(cur.value)
+        return st
+
+    def sync(self) -> N.SpxState:
+        return self.read_state()
+
+    def solve(self, max_pivots: int, check_every: int = 64):
+        while True:
+            st = self.run(check_every, check_every=check_every)
+            if st is None:
+                st = self.read_state()
+            if st.status != N.PIVOT or st.npiv >= max_pivots:
+                return int(st.status), int(st.npiv)
+
+    def local_body(self) -> torch.Tensor:
+        self.read_state()
+        return self.A[self._cur, :, : self.m_loc]
+
+    def b_current(self) -> torch.Tensor:
+        self.read_state()
+        return self.b[self._cur, : self.n]
+
+    def close(self):
+        if self.handle:
+            N.call("spx_fshard_close", self.handle)
+            self.handle = ctypes.c_void_p()
+        self.xbox.close()
+
+
 class PeerShardedTableau(ShardedTableau):
     """The sharded look-ahead loop enqueued from C (spx_shard_* handle, csrc/spx_shard.cu): per pivot
     no Python, no collective library — update k on the main stream, next b / candidate / NVLink peer

@@ -510,6 +510,38 @@ def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookah
             bx.close()
 
 
+@pytest.mark.parametrize("n,m,kind,depth", [(20, 700, "dense", 8), (33, 2500, "dense", 3), (12, 1300, "smallint", 8),
+                                            (9, 40, "smallint", 5), (300, 700, "dense", 8)])
+def test_fused_sharded_loop_single_rank(spx, n, m, kind, depth):
+    """The column-sharded fused loop (cooperative pricing with the in-kernel exchange) with ONE rank:
+    the whole code path except the cross-rank selection, against the oracle."""
+    from simplex_method_solver_b200 import parallel as P
+    if kind == "dense":
+        rows, c = W.dense_lp(n, m, 3)
+    else:
+        rng = np.random.default_rng(5)
+        rows = np.hstack([rng.integers(-3, 4, (n, m)).astype(float), rng.integers(-2, 7, (n, 1)).astype(float)])
+        c = rng.integers(-3, 4, m).astype(float)
+    cap = 45
+    o = oracle.solve(rows, c, max_pivots=cap)
+    sh = P.FusedShardedTableau(n, m, 0, 1, "cuda", trace_capacity=cap + 16, depth=depth)
+    try:
+        sh.load(rows, c, max_pivots=cap)
+        status, npiv = sh.solve(cap, check_every=7)
+        assert (status, npiv) == (o.status, o.npiv)
+        assert sh.trace[:npiv].cpu().numpy().tolist() == o.trace.tolist()
+        assert sh.rowlab.cpu().numpy().tolist() == o.rowlab.tolist()
+        assert sh.collab[:n].cpu().numpy().tolist() == o.collab.tolist()
+        body = sh.local_body().cpu().numpy()
+        ob = np.zeros((n + 1, m))
+        ob[:n] = o.table[: n * (m + 1)].reshape(n, m + 1)[:, :m]
+        ob[n] = o.table[n * (m + 1):]
+        assert np.array_equal(bits(body), bits(ob))
+        assert np.array_equal(bits(sh.b_current().cpu().numpy()), bits(o.table[: n * (m + 1)].reshape(n, m + 1)[:, m].copy()))
+    finally:
+        sh.close()
+
+
 # --------------------------------------------------------------------------- BASELINE configs
 @pytest.mark.parametrize("lookahead", [False, True, "resident", "fused", "fused-coop"])
 def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests, lookahead):

@@ -35,27 +35,29 @@ def _worker(rank, world, port, n, m, seed, cap, mode, out):
         from simplex_method_solver_b200 import parallel as P
         from simplex_method_solver_b200 import workloads as W
         rows, c = W.dense_lp(n, m, seed)
-        if mode == "p2p":
+        if mode == "fused":
+            sh = P.FusedShardedTableau(n, m, rank, world, dev, trace_capacity=cap + 8, depth=5)
+        elif mode == "p2p":
             sh = P.PeerShardedTableau(n, m, rank, world, dev, trace_capacity=cap + 8)
         else:
             sh = P.ShardedTableau(n, m, rank, world, dev, trace_capacity=cap + 8, lookahead=(mode == "nccl-ahead"))
         sh.load(rows, c, max_pivots=cap)
         status, npiv = sh.solve(cap, check_every=16)
         st = sh.sync()
-        body = sh.local_body().cpu().numpy().copy() if mode != "p2p" else \
+        body = sh.local_body().cpu().numpy().copy() if mode not in ("p2p",) else \
             sh.A[sh._cur, :, : sh.m_loc].cpu().numpy().copy()
         b = (sh.b[sh._cur, :n] if mode == "p2p" else sh.b_current()).cpu().numpy().copy()
         out.put((rank, {"status": int(st.status), "npiv": int(st.npiv), "col0": sh.col0, "body": body, "b": b,
                         "trace": sh.trace[: int(st.npiv)].cpu().numpy().copy(),
                         "rowlab": sh.rowlab.cpu().numpy().copy(), "collab": sh.collab[:n].cpu().numpy().copy()}))
         dist.barrier()
-        if mode == "p2p":
+        if mode in ("p2p", "fused"):
             sh.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["p2p", "nccl", "nccl-ahead"])
+@pytest.mark.parametrize("mode", ["fused", "p2p", "nccl", "nccl-ahead"])
 @pytest.mark.parametrize("n,m,cap", [(300, 2600, 150), (64, 1024, 400)])
 def test_sharded_flow_on_real_gpus(mode, n, m, cap):
     import torch
