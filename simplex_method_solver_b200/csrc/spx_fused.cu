@@ -38,6 +38,7 @@ constexpr int FUP_TC         = 2 * FUP_THREADS;
 constexpr int FUP_TR         = 32;     // rows per tile: the per-level row slices are amortised over 4 batches
 constexpr int FUP_UNROLL     = 8;
 constexpr int PRICE_BATCH    = 8;
+constexpr int COOP_THREADS   = 512;    // per CTA of the cooperative pricing kernels: fewer CTAs = cheaper grid barriers
 
 struct Level { int32_t r; int32_t c; double p; };
 struct alignas(128) PlanHeader {
@@ -233,7 +234,7 @@ struct CoopArgs {
     Ratio     *part;           // [FUSE_MAX][gridDim.x] ratio partials
 };
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(COOP_THREADS, 1)
 coop_price_kernel(CoopArgs ca) {
     cg::grid_group grid = cg::this_grid();
     const PriceArgs &a = ca.a;
@@ -507,7 +508,7 @@ __device__ void exchange_keys(const ShardArgs &sa, const XBoxLayout &XL, int lev
     }
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(COOP_THREADS, 1)
 shard_price_kernel(ShardArgs sa) {
     cg::grid_group grid = cg::this_grid();
     const CoopArgs &ca = sa.ca;
@@ -885,7 +886,7 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         g_coop_ctas = 0;
-        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_price_kernel, 256, 0) == cudaSuccess &&
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coop_price_kernel, COOP_THREADS, 0) == cudaSuccess &&
             per_sm > 0)
             g_coop_ctas = min(COOP_MAX_CTAS, sm_count());
     }
@@ -897,10 +898,10 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
     if (phase == 2) {
         // nothing to price
     } else if (coop) {
-        int G = (max(n + 1, (int)ld) + 255) / 256;
+        int G = (max(n + 1, (int)ld) + COOP_THREADS - 1) / COOP_THREADS;
         G = G > g_coop_ctas ? g_coop_ctas : (G < 1 ? 1 : G);
         void *args[] = {&ca};
-        e = cudaLaunchCooperativeKernel((const void *)coop_price_kernel, dim3(G), dim3(256), args, 0, stream);
+        e = cudaLaunchCooperativeKernel((const void *)coop_price_kernel, dim3(G), dim3(COOP_THREADS), args, 0, stream);
     } else {
         block_price_kernel<<<1, PRICE_THREADS, 0, stream>>>(a);
         e = cudaGetLastError();
@@ -959,15 +960,15 @@ cudaError_t fused_shard_pass(double *A0, double *A1, double *b0, double *b1, int
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         g_shard_ctas = 0;
-        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shard_price_kernel, 256, 0) == cudaSuccess &&
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, shard_price_kernel, COOP_THREADS, 0) == cudaSuccess &&
             per_sm > 0)
             g_shard_ctas = min(COOP_MAX_CTAS, sm_count());
     }
     if (g_shard_ctas <= 0) return cudaErrorNotSupported;
-    int G = (max(n + 1, (int)ld) + 255) / 256;
+    int G = (max(n + 1, (int)ld) + COOP_THREADS - 1) / COOP_THREADS;
     G = G > g_shard_ctas ? g_shard_ctas : (G < 1 ? 1 : G);
     void *args[] = {&sa};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)shard_price_kernel, dim3(G), dim3(256), args, 0, stream);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)shard_price_kernel, dim3(G), dim3(COOP_THREADS), args, 0, stream);
     if (e != cudaSuccess) return e;
     spx_host::count_launch();
     static bool configured = false;

@@ -481,6 +481,9 @@ class FusedShardedTableau(ShardedTableau):
             st = self.run(check_every, check_every=check_every)
             if st is None:
                 st = self.read_state()
+            if st.status == N.PIVOT and st.npiv >= st.max_pivots:
+                self.run(1)                      # the pricing of one more pass reports SPX_CAP or the real ending
+                st = self.read_state()
             if st.status != N.PIVOT or st.npiv >= max_pivots:
                 return int(st.status), int(st.npiv)
 
