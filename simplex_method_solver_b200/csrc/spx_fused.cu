@@ -790,7 +790,6 @@ update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cb
             for (int l = 0; l < f; ++l) {
                 const double2 rj = *reinterpret_cast<const double2 *>(&sm.rows[l][2 * tid]);
                 const PivotDiv d = s_lvl[l].d;
-                ok = ok && d.ok;
 #pragma unroll
                 for (int u = 0; u < FUP_UNROLL; ++u) {
                     const double ci = sm.cols[l][ii + u];
