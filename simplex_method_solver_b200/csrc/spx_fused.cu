@@ -46,6 +46,7 @@ struct alignas(128) PlanHeader {
     int32_t src;        // index (0/1) of the ping-pong buffer that holds the input table
     int32_t pad[2];
     Level   lvl[FUSE_MAX];
+    int32_t owner[FUSE_MAX];   // column-sharded: the rank whose plane holds COL_l (0 on one GPU)
 };
 
 struct LevelDiv { int r, c; PivotDiv d; };
@@ -182,7 +183,7 @@ block_price_kernel(PriceArgs a) {
         // ---- record the level, then advance the running b column and f row by it
         if (tid == 0) {
             s_lvl[i].r = r; s_lvl[i].c = c; s_lvl[i].d = pivot_div_prepare(p);
-            a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p;
+            a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p; a.plan->owner[i] = 0;
             const int32_t tmp = a.rowlab[c]; a.rowlab[c] = a.collab[r]; a.collab[r] = tmp;            // :152
             if (a.trace) { a.trace[2 * (npiv0 + i)] = r; a.trace[2 * (npiv0 + i) + 1] = c; }
         }
@@ -389,7 +390,7 @@ coop_price_kernel(CoopArgs ca) {
         if (tid == 0) {
             s_lvl[i].r = r; s_lvl[i].c = c; s_lvl[i].d = pivot_div_prepare(p);
             if (blockIdx.x == 0) {
-                a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p;
+                a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p; a.plan->owner[i] = 0;
                 const int32_t tmp = a.rowlab[c]; a.rowlab[c] = a.collab[r]; a.collab[r] = tmp;        // :152
                 if (a.trace) { a.trace[2 * (npiv0 + i)] = r; a.trace[2 * (npiv0 + i) + 1] = c; }
             }
@@ -418,13 +419,16 @@ coop_price_kernel(CoopArgs ca) {
 // ---- the cooperative pricing kernel for a COLUMN-SHARDED tableau (one process per GPU) ----------
 // Rank g owns the columns [col0, col0 + m) of the body; b, labels, state and the plan are replicated.
 // Per level the ranks exchange, straight from inside this kernel over NVLink peer memory:
-//   keys    every rank's best local entering column (16 B) -> every rank's XBOX key slots + flag;
-//   column  the OWNER of the winning column builds it (gather + replay) and its threads store the
-//           n+1 cells into every rank's COLS plane, then a flag; everyone else waits for the flag.
+//   column  every rank builds ITS best local entering column (gather + replay) and its threads store the
+//           n+1 cells into its plane in every rank's XBOX;
+//   key     then its 16-byte key + a release flag; every rank acquire-polls its local flags, takes the
+//           lexicographic minimum and reads the winner's plane.
 // The ratio test, the b column and the level bookkeeping are computed redundantly (bit-identically)
-// on every rank.  XBOX of one rank:  COLS[2][FUSE_MAX][cbd] | keys[FUSE_MAX+1][2][R][2] |
-// kflag[FUSE_MAX+1][2][R] | cflag[2][FUSE_MAX]  — COLS is double-buffered by pass parity because a fast
-// rank may price pass q+1 while a slow rank's update kernel still reads the planes of pass q.
+// on every rank.  XBOX of one rank:  COLS[2][FUSE_MAX][R][cbd] | keys[FUSE_MAX+1][2][R][2] |
+// kflag[FUSE_MAX+1][2][R]  — one plane per (level, source rank): every rank that has a candidate stores
+// its candidate column SPECULATIVELY together with its key (one exchange per level instead of a key
+// round followed by a column round); COLS is double-buffered by pass parity because a fast rank may
+// price pass q+1 while a slow rank's update kernel still reads the planes of pass q.
 constexpr int XB_MAX_RANKS = 16;
 
 struct XBoxLayout {
@@ -433,10 +437,10 @@ struct XBoxLayout {
 __host__ __device__ inline XBoxLayout xbox_layout(int64_t cbd, int R) {
     XBoxLayout L;
     L.cols_off = 0;
-    L.keys_off = (2LL * FUSE_MAX * cbd * 8 + 127) / 128 * 128;
+    L.keys_off = (2LL * FUSE_MAX * R * cbd * 8 + 127) / 128 * 128;
     L.kflag_off = L.keys_off + ((int64_t)(FUSE_MAX + 1) * 2 * R * 16 + 127) / 128 * 128;
-    L.cflag_off = L.kflag_off + ((int64_t)(FUSE_MAX + 1) * 2 * R * 8 + 127) / 128 * 128;
-    L.bytes = L.cflag_off + (2LL * FUSE_MAX * 8 + 127) / 128 * 128;
+    L.cflag_off = 0;
+    L.bytes = L.kflag_off + ((int64_t)(FUSE_MAX + 1) * 2 * R * 8 + 127) / 128 * 128;
     return L;
 }
 
@@ -521,8 +525,9 @@ shard_price_kernel(ShardArgs sa) {
     const int64_t ld = a.ld, cbd = a.cbd, col0 = sa.col0;
     const XBoxLayout XL = xbox_layout(cbd, sa.R);
     const int par = (int)(sa.seq & 1ull);
-    // this pass's COLS planes in MY box (every rank fills its own copy from the owners' stores)
-    double *COLS = reinterpret_cast<double *>(sa.xbox[sa.rank] + XL.cols_off) + (int64_t)par * FUSE_MAX * cbd;
+    // this pass's COLS planes in MY box: plane (level l, source rank g) at COLS + (l * R + g) * cbd
+    double *COLS = reinterpret_cast<double *>(sa.xbox[sa.rank] + XL.cols_off) + (int64_t)par * FUSE_MAX * sa.R * cbd;
+    __shared__ const double *s_colp[FUSE_MAX];           // per chosen level: the winner's plane
     int *gsel = &ca.cs->idx[FUSE_MAX][0];               // CTA 0 -> grid: {column, owner, timeout} of the last exchange
 
     if (a.st->status != SPX_PIVOT) {                     // uniform over the grid AND over the ranks
@@ -558,7 +563,7 @@ shard_price_kernel(ShardArgs sa) {
         } else {
             const LevelDiv L = s_lvl[i - 1];             // L.c is the LOCAL index of the pivot column or -1
             const double *bin = ca.bv[(i - 1) & 1];
-            const double *COLL = COLS + (int64_t)(i - 1) * cbd;
+            const double *COLL = s_colp[i - 1];
             const double br = __ldcg(bin + L.r), fc = __ldcg(COLL + n);
             for (int t = gtid; t < n; t += gn) {
                 const double bt = __ldcg(bin + t);
@@ -566,7 +571,7 @@ shard_price_kernel(ShardArgs sa) {
                 bout[t] = v;
                 if (v < 0.0) bneg = min(bneg, t);
             }
-            if (tid < i - 1) s_scal[tid] = __ldcg(COLS + (int64_t)tid * cbd + L.r);
+            if (tid < i - 1) s_scal[tid] = __ldcg(s_colp[tid] + L.r);
             __syncthreads();
             double *ROWL = a.ROWS + (int64_t)(i - 1) * ld;
             const double *rowp = A + (int64_t)L.r * ld;
@@ -602,7 +607,7 @@ shard_price_kernel(ShardArgs sa) {
         if (r1 >= 0) {
             // phase-1: first positive cell of the local part of the virtual row r1 (:82-85)
             kind = 1;
-            if (tid < i) s_scal[tid] = __ldcg(COLS + (int64_t)tid * cbd + r1);
+            if (tid < i) s_scal[tid] = __ldcg(s_colp[tid] + r1);
             __syncthreads();
             const double *row = A + (int64_t)r1 * ld;
             int loc = SPX_NONE;
@@ -628,7 +633,22 @@ shard_price_kernel(ShardArgs sa) {
             cloc = __ldcg(&ca.cs->idx[i][2]);
             kh = best;
         }
-        // ---------------- exchange the keys, pick the global entering column and its owner
+        // ---------------- phase B: this rank's candidate column of the virtual table, stored straight
+        // into its plane in EVERY rank's XBOX (speculative: only the winner's plane will be read)
+        if (cloc != SPX_NONE) {
+            if (tid < i) s_scal[tid] = __ldcg(a.ROWS + (int64_t)tid * ld + cloc);
+            __syncthreads();
+            const int64_t plane = (((int64_t)par * FUSE_MAX + i) * sa.R + sa.rank) * cbd;
+            for (int t = gtid; t <= n; t += gn) {
+                double w = A[(int64_t)t * ld + cloc];
+                for (int l = 0; l < i; ++l) w = apply_level(w, t, cloc, s_lvl[l], s_scal[l], __ldcg(s_colp[l] + t));
+                for (int g = 0; g < sa.R; ++g)
+                    (reinterpret_cast<double *>(sa.xbox[g] + XL.cols_off) + plane)[t] = w;
+            }
+        }
+        __threadfence_system();
+        grid.sync();
+        // ---------------- one exchange: key + flag (the column stores above are ordered before the flag)
         if (blockIdx.x == 0)
             exchange_keys(sa, XL, i, kind, (cloc == SPX_NONE) ? ~0ull : kh,
                           (cloc == SPX_NONE) ? ~0ull : (unsigned long long)(col0 + cloc), gsel);
@@ -638,32 +658,11 @@ shard_price_kernel(ShardArgs sa) {
         if (c == SPX_NONE) { status = (r1 >= 0) ? SPX_INCORRECT : SPX_OPTIMAL; phase1 = (r1 >= 0); f = i; break; }
         const int64_t cl64 = (int64_t)c - col0;
         const int clocal = (cl64 >= 0 && cl64 < m) ? (int)cl64 : -1;
-
-        // ---------------- phase B: the owner builds the column and stores it into every rank's plane
-        if (owner == sa.rank) {
-            if (tid < i) s_scal[tid] = __ldcg(a.ROWS + (int64_t)tid * ld + clocal);
-            __syncthreads();
-            for (int t = gtid; t <= n; t += gn) {
-                double w = A[(int64_t)t * ld + clocal];
-                for (int l = 0; l < i; ++l) w = apply_level(w, t, clocal, s_lvl[l], s_scal[l], __ldcg(COLS + (int64_t)l * cbd + t));
-                for (int g = 0; g < sa.R; ++g)
-                    (reinterpret_cast<double *>(sa.xbox[g] + XL.cols_off) + ((int64_t)par * FUSE_MAX + i) * cbd)[t] = w;
-            }
-            __threadfence_system();
-            grid.sync();
-            if (blockIdx.x == 0 && tid < sa.R)
-                st_release_sys(reinterpret_cast<unsigned long long *>(sa.xbox[tid] + XL.cflag_off) + par * FUSE_MAX + i, sa.seq);
-        }
-        if (blockIdx.x == 0 && tid == 0) {
-            const unsigned long long *fl = reinterpret_cast<const unsigned long long *>(sa.xbox[sa.rank] + XL.cflag_off) +
-                                           par * FUSE_MAX + i;
-            gsel[3] = wait_seq(fl, sa.seq) ? 0 : 1;
-        }
-        grid.sync();
-        if (__ldcg(gsel + 3)) { status = SPX_PEER_TIMEOUT; f = i; break; }
+        if (tid == 0) s_colp[i] = COLS + ((int64_t)i * sa.R + owner) * cbd;
+        __syncthreads();
 
         // ---------------- ratio fold on the received column (every rank, identical) (:107-136)
-        double *COLi = COLS + (int64_t)i * cbd;
+        const double *COLi = s_colp[i];
         Ratio q = ratio_identity();
         if (r1 < 0)
             for (int t = gtid; t < n; t += gn) ratio_accumulate(q, t, __ldcg(COLi + t), bout[t]);
@@ -698,6 +697,7 @@ shard_price_kernel(ShardArgs sa) {
             s_lvl[i].r = r; s_lvl[i].c = clocal; s_lvl[i].d = pivot_div_prepare(p);
             if (blockIdx.x == 0) {
                 a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p;       // GLOBAL column in the plan
+                a.plan->owner[i] = owner;
                 const int32_t tmp = a.rowlab[c]; a.rowlab[c] = a.collab[r]; a.collab[r] = tmp;
                 if (a.trace) { a.trace[2 * (npiv0 + i)] = r; a.trace[2 * (npiv0 + i) + 1] = c; }
             }
@@ -730,7 +730,7 @@ struct FusedSmem {
 
 template <int MINB>
 __global__ void __launch_bounds__(FUP_THREADS, MINB)
-update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0,
+update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R,
                     const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
                     const double *__restrict__ COLS) {
     const int f = plan->f;
@@ -756,7 +756,7 @@ update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cb
         mbar_expect_tx(&s_bar, (uint32_t)f * (row_bytes + col_bytes));
         for (int l = 0; l < f; ++l) {
             bulk_g2s(sm.rows[l], ROWS + (int64_t)l * ld + j0, row_bytes, &s_bar);
-            bulk_g2s(sm.cols[l], COLS + (int64_t)l * cbd + i0, col_bytes, &s_bar);
+            bulk_g2s(sm.cols[l], COLS + ((int64_t)l * R + plan->owner[l]) * cbd + i0, col_bytes, &s_bar);
         }
     }
     if (tid < f) {
@@ -917,9 +917,9 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
     }
     dim3 grid((unsigned)((m + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + FUP_TR - 1) / FUP_TR));
     switch (minb) {
-    case 2: update_fused_kernel<2><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, col0, plan, ROWS, COLS); break;
-    case 3: update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, col0, plan, ROWS, COLS); break;
-    default: update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, col0, plan, ROWS, COLS); break;
+    case 2: update_fused_kernel<2><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, col0, 1, plan, ROWS, COLS); break;
+    case 3: update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, col0, 1, plan, ROWS, COLS); break;
+    default: update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m, ld, cbd, col0, 1, plan, ROWS, COLS); break;
     }
     spx_host::count_launch();
     return cudaGetLastError();
@@ -978,13 +978,13 @@ cudaError_t fused_shard_pass(double *A0, double *A1, double *b0, double *b1, int
     }
     const XBoxLayout XL = xbox_layout(cbd, R);
     const double *COLS = reinterpret_cast<const double *>(static_cast<unsigned char *>(xboxes[rank]) + XL.cols_off) +
-                         (int64_t)(seq & 1ull) * FUSE_MAX * cbd;
+                         (int64_t)(seq & 1ull) * FUSE_MAX * R * cbd;
     dim3 grid((unsigned)((m_loc + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + FUP_TR - 1) / FUP_TR));
     if (grid.x == 0) return cudaSuccess;                     // a shard without columns only prices
     if (minb == 3)
-        update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m_loc, ld, cbd, col0, plan, ROWS, COLS);
+        update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m_loc, ld, cbd, col0, R, plan, ROWS, COLS);
     else
-        update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m_loc, ld, cbd, col0, plan, ROWS, COLS);
+        update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m_loc, ld, cbd, col0, R, plan, ROWS, COLS);
     spx_host::count_launch();
     return cudaGetLastError();
 }
