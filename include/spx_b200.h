@@ -96,6 +96,7 @@ int64_t     spx_launch_count(int reset);
 #define SPX_OPT_PIPE_ORDER       3  /* pipelined kernel tile order: 0 chunked column-major, 1 interleaved row-major */
 #define SPX_OPT_PIPE_GRID        4  /* pipelined kernel CTAs (0 = one per SM) */
 #define SPX_OPT_TILED_ROWS       5  /* tiled kernel rows per tile (0 = auto; else a multiple of 8 <= 64) */
+#define SPX_OPT_FUSE_LOOKAHEAD   9  /* fused loop in spx_solve: 0/1 price pass q+1 on a side stream during update q (default), 2 off */
 #define SPX_OPT_FUSE_PRICING     8  /* fused loop pricing kernel: 0 auto, 1 one CTA, 2 whole-GPU cooperative */
 #define SPX_OPT_FUSE_MIN_BLOCKS  7  /* fused update kernel: resident CTAs per SM its register budget targets (2..4, 0 = default) */
 #define SPX_OPT_FUSE_DEPTH       6  /* fused loop: pivots applied per pass over the body (0 = default 8, max 8) */
@@ -308,6 +309,9 @@ int spx_fshard_open(spx_fshard **out, int32_t rank, int32_t nranks, int32_t n, i
                     int64_t col0, int32_t rule, double *d_A0, double *d_A1, double *d_b0, double *d_b1,
                     spx_state *d_state, void *d_work, int64_t work_bytes, int32_t *d_rowlab, int32_t *d_collab,
                     int32_t *d_trace, void *const *xboxes);
+/* look-ahead (default on): the pricing of pass q+1 runs on the handle's high-priority side stream while
+ * the update of pass q streams; off: price, update, price, ... on `stream`. */
+int spx_fshard_set_lookahead(spx_fshard *h, int32_t on);
 int spx_fshard_enqueue(spx_fshard *h, int64_t pivots, int32_t depth, void *stream);
 int spx_fshard_read(spx_fshard *h, spx_state *h_state, int32_t *cur_buffer, void *stream);
 int spx_fshard_close(spx_fshard *h);

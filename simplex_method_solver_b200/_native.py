@@ -104,6 +104,7 @@ SIGNATURES = {
     "spx_fshard_xbox_bytes": (_i64, [_i32, _i32]),
     "spx_fshard_open": (ctypes.c_int, [ctypes.POINTER(_vp), _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _vp, _vp, _vp,
                                        _vp, _vp, _i64, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
+    "spx_fshard_set_lookahead": (ctypes.c_int, [_vp, _i32]),
     "spx_fshard_enqueue": (ctypes.c_int, [_vp, _i64, _i32, _vp]),
     "spx_fshard_read": (ctypes.c_int, [_vp, _vp, _pi32, _vp]),
     "spx_fshard_close": (ctypes.c_int, [_vp]),

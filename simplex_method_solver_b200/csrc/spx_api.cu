@@ -35,6 +35,9 @@ int fuse_max();
 int64_t fused_workspace_bytes(int, int64_t);
 cudaError_t fused_pass(double *, double *, double *, double *, int, int, int64_t, int, int, int, int, int, spx_state *,
                        void *, int32_t *, int32_t *, int32_t *, cudaStream_t);
+cudaError_t fused_solve_passes(double *, double *, double *, double *, int, int, int64_t, int, spx_state *, void *,
+                               int32_t *, int32_t *, int32_t *, int64_t, int, int, bool, cudaStream_t);
+cudaError_t fused_solo_sync();
 int64_t get_option(int);
 int     set_option(int, int64_t);
 cudaError_t selftest_division(const double *, const double *, int64_t, int64_t, unsigned long long *,
@@ -366,17 +369,15 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
             int F = (int)spx_launch::get_option(SPX_OPT_FUSE_DEPTH);
             if (F <= 0) F = 8;
             if (F > spx_launch::fuse_max()) F = spx_launch::fuse_max();
-            int64_t left = k;
-            while (left > 0) {
-                const int Fp = (int)(left < F ? left : F);
-                if (check(spx_launch::fused_pass(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, Fp,
-                                                 (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS),
-                                                 (int)spx_launch::get_option(SPX_OPT_FUSE_PRICING), 0, d_state, d_work, d_rowlab,
-                                                 d_collab, d_trace, s), "fused pass launch")) return -1;
-                left -= Fp;
-            }
+            // look-ahead (default): the pricing of pass q+1 runs on a side stream during the update of pass q
+            const bool la = spx_launch::get_option(SPX_OPT_FUSE_LOOKAHEAD) != 2;
+            if (check(spx_launch::fused_solve_passes(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, d_state, d_work, d_rowlab,
+                                                     d_collab, d_trace, k, F,
+                                                     (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS), la, s),
+                      "fused pass launch")) return -1;
             if (check(cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, s), "read state")) return -1;
             if (check(cudaStreamSynchronize(s), "fused passes")) return -1;
+            if (check(spx_launch::fused_solo_sync(), "fused side stream")) return -1;
             done += hs.npiv - base;
             continue;
         }

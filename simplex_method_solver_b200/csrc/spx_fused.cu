@@ -450,6 +450,8 @@ struct ShardArgs {
     int64_t col0;
     unsigned long long seq;      // pass number (1, 2, ...): the value the flags of this pass carry
     unsigned char *xbox[XB_MAX_RANKS];   // every rank's XBOX mapped into this process ([rank] = local)
+    const PlanHeader *prev_plan;         // look-ahead: the plan of the pass whose update is still running (else null)
+    const double *prev_ROWS;             //             and its ROW planes
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -518,8 +520,11 @@ shard_price_kernel(ShardArgs sa) {
     const CoopArgs &ca = sa.ca;
     const PriceArgs &a = ca.a;
     __shared__ Scratch s;
-    __shared__ LevelDiv s_lvl[FUSE_MAX];
-    __shared__ double s_scal[FUSE_MAX];
+    // look-ahead: levels 0..np-1 are the PREVIOUS pass's (still being applied to the stored table by its
+    // update kernel while this kernel runs), levels np..np+i-1 are this pass's
+    __shared__ LevelDiv s_lvl[2 * FUSE_MAX];
+    __shared__ double s_scal[2 * FUSE_MAX];
+    __shared__ const double *s_rowp[2 * FUSE_MAX];       // per level: its ROW plane (local columns)
     const int n = a.n, m = a.m, tid = threadIdx.x;
     const int G = gridDim.x, gtid = blockIdx.x * blockDim.x + tid, gn = G * blockDim.x;
     const int64_t ld = a.ld, cbd = a.cbd, col0 = sa.col0;
@@ -527,16 +532,30 @@ shard_price_kernel(ShardArgs sa) {
     const int par = (int)(sa.seq & 1ull);
     // this pass's COLS planes in MY box: plane (level l, source rank g) at COLS + (l * R + g) * cbd
     double *COLS = reinterpret_cast<double *>(sa.xbox[sa.rank] + XL.cols_off) + (int64_t)par * FUSE_MAX * sa.R * cbd;
-    __shared__ const double *s_colp[FUSE_MAX];           // per chosen level: the winner's plane
+    __shared__ const double *s_colp[2 * FUSE_MAX];       // per level: the winner's COL plane in MY box
     int *gsel = &ca.cs->idx[FUSE_MAX][0];               // CTA 0 -> grid: {column, owner, timeout} of the last exchange
 
     if (a.st->status != SPX_PIVOT) {                     // uniform over the grid AND over the ranks
         if (gtid == 0) a.plan->f = 0;
         return;
     }
+    // cur = the buffer this pass's INPUT table lives in (it may still be under construction by the
+    // previous pass's update); the cells are gathered from the last MATERIALISED table: the other buffer
+    // when np levels of the previous pass are pending, cur itself otherwise
     const int cur = (int)a.st->reserved[0] & 1;
-    const double *A = a.A[cur];
+    const int np = (sa.prev_plan != nullptr) ? sa.prev_plan->f : 0;
+    const double *A = a.A[np > 0 ? (cur ^ 1) : cur];
     const int64_t npiv0 = a.st->npiv, cap = a.st->max_pivots;
+    if (tid < np) {
+        const int64_t cl = (int64_t)sa.prev_plan->lvl[tid].c - col0;
+        s_lvl[tid].r = sa.prev_plan->lvl[tid].r;
+        s_lvl[tid].c = (cl >= 0 && cl < m) ? (int)cl : -1;
+        s_lvl[tid].d = pivot_div_prepare(sa.prev_plan->lvl[tid].p);
+        s_rowp[tid] = sa.prev_ROWS + (int64_t)tid * ld;
+        s_colp[tid] = reinterpret_cast<const double *>(sa.xbox[sa.rank] + XL.cols_off) +
+                      (((int64_t)(par ^ 1) * FUSE_MAX + tid) * sa.R + sa.prev_plan->owner[tid]) * cbd;
+    }
+    __syncthreads();
 
     if (blockIdx.x == 0)
         for (int k = tid; k < (FUSE_MAX + 1) * 4; k += blockDim.x) {
@@ -556,14 +575,15 @@ shard_price_kernel(ShardArgs sa) {
         if (i == 0) {
             for (int t = gtid; t < n; t += gn) { const double v = a.b[cur][t]; bout[t] = v; if (v < 0.0) bneg = min(bneg, t); }
             for (int j = gtid; j < m; j += gn) {
-                const double v = A[(int64_t)n * ld + j];
+                // np > 0: the previous pricing left the running f row at exactly this table
+                const double v = (np > 0) ? a.frow[j] : A[(int64_t)n * ld + j];
                 a.frow[j] = v;
                 if (v < 0.0) { fneg = min(fneg, j); const unsigned long long k = orderable(v); fkey = k < fkey ? k : fkey; }
             }
         } else {
-            const LevelDiv L = s_lvl[i - 1];             // L.c is the LOCAL index of the pivot column or -1
+            const LevelDiv L = s_lvl[np + i - 1];        // L.c is the LOCAL index of the pivot column or -1
             const double *bin = ca.bv[(i - 1) & 1];
-            const double *COLL = s_colp[i - 1];
+            const double *COLL = s_colp[np + i - 1];
             const double br = __ldcg(bin + L.r), fc = __ldcg(COLL + n);
             for (int t = gtid; t < n; t += gn) {
                 const double bt = __ldcg(bin + t);
@@ -571,15 +591,15 @@ shard_price_kernel(ShardArgs sa) {
                 bout[t] = v;
                 if (v < 0.0) bneg = min(bneg, t);
             }
-            if (tid < i - 1) s_scal[tid] = __ldcg(s_colp[tid] + L.r);
+            if (tid < np + i - 1) s_scal[tid] = __ldcg(s_colp[tid] + L.r);
             __syncthreads();
             double *ROWL = a.ROWS + (int64_t)(i - 1) * ld;
             const double *rowp = A + (int64_t)L.r * ld;
             for (int j = gtid; j < ld; j += gn) {
                 if (j >= m) { ROWL[j] = 0.0; continue; }
                 double rv = rowp[j];
-                for (int l = 0; l < i - 1; ++l)
-                    rv = apply_level(rv, L.r, j, s_lvl[l], __ldcg(a.ROWS + (int64_t)l * ld + j), s_scal[l]);
+                for (int l = 0; l < np + i - 1; ++l)
+                    rv = apply_level(rv, L.r, j, s_lvl[l], __ldcg(s_rowp[l] + j), s_scal[l]);
                 ROWL[j] = rv;
                 const double fj = a.frow[j];
                 const double v = (j == L.c) ? pivot_div(fc, L.d) : cell_update(fj, L.d, rv, fc);
@@ -607,13 +627,13 @@ shard_price_kernel(ShardArgs sa) {
         if (r1 >= 0) {
             // phase-1: first positive cell of the local part of the virtual row r1 (:82-85)
             kind = 1;
-            if (tid < i) s_scal[tid] = __ldcg(s_colp[tid] + r1);
+            if (tid < np + i) s_scal[tid] = __ldcg(s_colp[tid] + r1);
             __syncthreads();
             const double *row = A + (int64_t)r1 * ld;
             int loc = SPX_NONE;
             for (int j = gtid; j < m; j += gn) {
                 double v = row[j];
-                for (int l = 0; l < i; ++l) v = apply_level(v, r1, j, s_lvl[l], __ldcg(a.ROWS + (int64_t)l * ld + j), s_scal[l]);
+                for (int l = 0; l < np + i; ++l) v = apply_level(v, r1, j, s_lvl[l], __ldcg(s_rowp[l] + j), s_scal[l]);
                 if (v > 0.0) { loc = j; break; }
             }
             loc = block_min_int(loc, s);
@@ -636,12 +656,12 @@ shard_price_kernel(ShardArgs sa) {
         // ---------------- phase B: this rank's candidate column of the virtual table, stored straight
         // into its plane in EVERY rank's XBOX (speculative: only the winner's plane will be read)
         if (cloc != SPX_NONE) {
-            if (tid < i) s_scal[tid] = __ldcg(a.ROWS + (int64_t)tid * ld + cloc);
+            if (tid < np + i) s_scal[tid] = __ldcg(s_rowp[tid] + cloc);
             __syncthreads();
             const int64_t plane = (((int64_t)par * FUSE_MAX + i) * sa.R + sa.rank) * cbd;
             for (int t = gtid; t <= n; t += gn) {
                 double w = A[(int64_t)t * ld + cloc];
-                for (int l = 0; l < i; ++l) w = apply_level(w, t, cloc, s_lvl[l], s_scal[l], __ldcg(s_colp[l] + t));
+                for (int l = 0; l < np + i; ++l) w = apply_level(w, t, cloc, s_lvl[l], s_scal[l], __ldcg(s_colp[l] + t));
                 for (int g = 0; g < sa.R; ++g)
                     (reinterpret_cast<double *>(sa.xbox[g] + XL.cols_off) + plane)[t] = w;
             }
@@ -658,11 +678,14 @@ shard_price_kernel(ShardArgs sa) {
         if (c == SPX_NONE) { status = (r1 >= 0) ? SPX_INCORRECT : SPX_OPTIMAL; phase1 = (r1 >= 0); f = i; break; }
         const int64_t cl64 = (int64_t)c - col0;
         const int clocal = (cl64 >= 0 && cl64 < m) ? (int)cl64 : -1;
-        if (tid == 0) s_colp[i] = COLS + ((int64_t)i * sa.R + owner) * cbd;
+        if (tid == 0) {
+            s_colp[np + i] = COLS + ((int64_t)i * sa.R + owner) * cbd;
+            s_rowp[np + i] = a.ROWS + (int64_t)i * ld;
+        }
         __syncthreads();
 
         // ---------------- ratio fold on the received column (every rank, identical) (:107-136)
-        const double *COLi = s_colp[i];
+        const double *COLi = s_colp[np + i];
         Ratio q = ratio_identity();
         if (r1 < 0)
             for (int t = gtid; t < n; t += gn) ratio_accumulate(q, t, __ldcg(COLi + t), bout[t]);
@@ -694,7 +717,7 @@ shard_price_kernel(ShardArgs sa) {
         if (npiv0 + i >= cap) { status = SPX_CAP; last_r = r; last_c = c; last_p = p; f = i; break; }
         __syncthreads();
         if (tid == 0) {
-            s_lvl[i].r = r; s_lvl[i].c = clocal; s_lvl[i].d = pivot_div_prepare(p);
+            s_lvl[np + i].r = r; s_lvl[np + i].c = clocal; s_lvl[np + i].d = pivot_div_prepare(p);
             if (blockIdx.x == 0) {
                 a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p;       // GLOBAL column in the plan
                 a.plan->owner[i] = owner;
@@ -844,16 +867,41 @@ int fuse_max() { return FUSE_MAX; }
 
 static inline int64_t align128(int64_t v) { return (v + 127) / 128 * 128; }
 
-// workspace: plan header | ROWS[FUSE_MAX][ld] | COLS[FUSE_MAX][cbd] | frow[ld] | bvec[n] | bvec2[n] |
-//            CoopScratch | ratio partials [FUSE_MAX][COOP_MAX_CTAS]
+// workspace: plan[2] | ROWS[2][FUSE_MAX][ld] | COLS[FUSE_MAX][cbd] | frow[ld] | bvec[n] | bvec2[n] | CoopScratch |
+//            ratio partials [FUSE_MAX][COOP_MAX_CTAS] | a one-rank XBOX (the look-ahead loop on ONE GPU runs
+//            the sharded pricing kernel with R = 1).  plan/ROWS are double-buffered by pass parity: the
+//            pricing of pass q+1 writes one set while the update of pass q reads the other.
 constexpr int COOP_MAX_CTAS = 160;
 
-int64_t fused_workspace_bytes(int n, int64_t ld) {
+struct FusedWork {
+    PlanHeader *plan[2];
+    double *ROWS[2];
+    double *COLS, *frow, *bvec, *bvec2;
+    CoopScratch *cs;
+    Ratio *part;
+    unsigned char *xbox1;
+    int64_t bytes;
+};
+
+FusedWork carve_work(void *work, int n, int64_t ld) {
     const int64_t cbd = colbuf_doubles(n);
-    return align128(sizeof(PlanHeader)) + align128(FUSE_MAX * ld * 8) + align128(FUSE_MAX * cbd * 8) +
-           align128(ld * 8) + 2 * align128(((int64_t)n + 16) * 8) + align128(sizeof(CoopScratch)) +
-           align128((int64_t)FUSE_MAX * COOP_MAX_CTAS * sizeof(Ratio));
+    char *p = static_cast<char *>(work);
+    char *p0 = p;
+    FusedWork w;
+    for (int h = 0; h < 2; ++h) { w.plan[h] = reinterpret_cast<PlanHeader *>(p); p += align128(sizeof(PlanHeader)); }
+    for (int h = 0; h < 2; ++h) { w.ROWS[h] = reinterpret_cast<double *>(p); p += align128(FUSE_MAX * ld * 8); }
+    w.COLS = reinterpret_cast<double *>(p);   p += align128(FUSE_MAX * cbd * 8);
+    w.frow = reinterpret_cast<double *>(p);   p += align128(ld * 8);
+    w.bvec = reinterpret_cast<double *>(p);   p += align128(((int64_t)n + 16) * 8);
+    w.bvec2 = reinterpret_cast<double *>(p);  p += align128(((int64_t)n + 16) * 8);
+    w.cs = reinterpret_cast<CoopScratch *>(p); p += align128(sizeof(CoopScratch));
+    w.part = reinterpret_cast<Ratio *>(p);    p += align128((int64_t)FUSE_MAX * COOP_MAX_CTAS * sizeof(Ratio));
+    w.xbox1 = reinterpret_cast<unsigned char *>(p); p += align128(xbox_layout(cbd, 1).bytes);
+    w.bytes = p - p0;
+    return w;
 }
+
+int64_t fused_workspace_bytes(int n, int64_t ld) { return carve_work(nullptr, n, ld).bytes; }
 
 static int g_coop_ctas = -1;      // co-resident CTAs of coop_price_kernel (0: cooperative launch unavailable)
 
@@ -864,15 +912,11 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
     if (F < 1) F = 1;
     if (F > FUSE_MAX) F = FUSE_MAX;
     const int64_t cbd = colbuf_doubles(n);
-    char *p = static_cast<char *>(work);
-    PlanHeader *plan = reinterpret_cast<PlanHeader *>(p);       p += align128(sizeof(PlanHeader));
-    double *ROWS = reinterpret_cast<double *>(p);               p += align128(FUSE_MAX * ld * 8);
-    double *COLS = reinterpret_cast<double *>(p);               p += align128(FUSE_MAX * cbd * 8);
-    double *frow = reinterpret_cast<double *>(p);               p += align128(ld * 8);
-    double *bvec = reinterpret_cast<double *>(p);               p += align128(((int64_t)n + 16) * 8);
-    double *bvec2 = reinterpret_cast<double *>(p);              p += align128(((int64_t)n + 16) * 8);
-    CoopScratch *cs = reinterpret_cast<CoopScratch *>(p);       p += align128(sizeof(CoopScratch));
-    Ratio *part = reinterpret_cast<Ratio *>(p);
+    const FusedWork w = carve_work(work, n, ld);
+    PlanHeader *plan = w.plan[0];
+    double *ROWS = w.ROWS[0], *COLS = w.COLS, *frow = w.frow, *bvec = w.bvec, *bvec2 = w.bvec2;
+    CoopScratch *cs = w.cs;
+    Ratio *part = w.part;
     CoopArgs ca;
     PriceArgs &a = ca.a;
     a.A[0] = A0; a.A[1] = A1; a.b[0] = b0; a.b[1] = b1;
@@ -927,33 +971,53 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
 
 static int g_shard_ctas = -1;
 
-// one pass of the column-sharded fused loop on this rank: cooperative pricing with the in-kernel
-// NVLink exchange, then the fused update of the local columns
-cudaError_t fused_shard_pass(double *A0, double *A1, double *b0, double *b1, int n, int m_loc, int64_t ld, int64_t col0,
-                             int rule, int F, int minb, spx_state *st, void *work, int32_t *rowlab, int32_t *collab,
-                             int32_t *trace, int rank, int R, unsigned long long seq, void *const *xboxes,
-                             cudaStream_t stream) {
-    if (F < 1) F = 1;
-    if (F > FUSE_MAX) F = FUSE_MAX;
-    const int64_t cbd = colbuf_doubles(n);
-    char *p = static_cast<char *>(work);
-    PlanHeader *plan = reinterpret_cast<PlanHeader *>(p);       p += align128(sizeof(PlanHeader));
-    double *ROWS = reinterpret_cast<double *>(p);               p += align128(FUSE_MAX * ld * 8);
-    p += align128(FUSE_MAX * cbd * 8);                          // (the COLS planes live in the XBOX instead)
-    double *frow = reinterpret_cast<double *>(p);               p += align128(ld * 8);
-    double *bvec = reinterpret_cast<double *>(p);               p += align128(((int64_t)n + 16) * 8);
-    double *bvec2 = reinterpret_cast<double *>(p);              p += align128(((int64_t)n + 16) * 8);
-    CoopScratch *cs = reinterpret_cast<CoopScratch *>(p);       p += align128(sizeof(CoopScratch));
-    Ratio *part = reinterpret_cast<Ratio *>(p);
+// Everything one rank needs to run fused passes (also used with R = 1 by spx_solve on one GPU)
+struct FusedCtx {
+    double *A[2], *b[2];
+    int n, m_loc, rule, rank, R;
+    int64_t ld, col0;
+    spx_state *st;
+    void *work;
+    int32_t *rowlab, *collab, *trace;
+    void *xbox[XB_MAX_RANKS];
+    unsigned long long seq;              // passes issued so far (flags carry it; parity = buffer set)
+    cudaStream_t side;                   // look-ahead: the pricing stream (high priority)
+    cudaEvent_t ev_start, ev_priced[2], ev_upd[2];
+};
+
+cudaError_t fused_ctx_streams(FusedCtx &c) {
+    int lo = 0, hi = 0;
+    cudaError_t e;
+    if ((e = cudaDeviceGetStreamPriorityRange(&lo, &hi)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
+    cudaEvent_t *evs[5] = {&c.ev_start, &c.ev_priced[0], &c.ev_priced[1], &c.ev_upd[0], &c.ev_upd[1]};
+    for (cudaEvent_t *ev : evs)
+        if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+void fused_ctx_destroy(FusedCtx &c) {
+    if (!c.side) return;
+    cudaStreamSynchronize(c.side);
+    cudaEventDestroy(c.ev_start);
+    for (int h = 0; h < 2; ++h) { cudaEventDestroy(c.ev_priced[h]); cudaEventDestroy(c.ev_upd[h]); }
+    cudaStreamDestroy(c.side);
+    c.side = nullptr;
+}
+
+static cudaError_t launch_shard_price(const FusedCtx &c, const FusedWork &w, int F, int h, bool with_prev,
+                                      cudaStream_t stream) {
     ShardArgs sa;
     PriceArgs &a = sa.ca.a;
-    a.A[0] = A0; a.A[1] = A1; a.b[0] = b0; a.b[1] = b1;
-    a.n = n; a.m = m_loc; a.ld = ld; a.cbd = cbd; a.rule = rule; a.F = F;
-    a.st = st; a.plan = plan; a.ROWS = ROWS; a.COLS = nullptr; a.frow = frow; a.bvec = bvec;
-    a.rowlab = rowlab; a.collab = collab; a.trace = trace;
-    sa.ca.bv[0] = bvec; sa.ca.bv[1] = bvec2; sa.ca.cs = cs; sa.ca.part = part;
-    sa.rank = rank; sa.R = R; sa.col0 = col0; sa.seq = seq;
-    for (int g = 0; g < XB_MAX_RANKS; ++g) sa.xbox[g] = g < R ? static_cast<unsigned char *>(xboxes[g]) : nullptr;
+    a.A[0] = c.A[0]; a.A[1] = c.A[1]; a.b[0] = c.b[0]; a.b[1] = c.b[1];
+    a.n = c.n; a.m = c.m_loc; a.ld = c.ld; a.cbd = colbuf_doubles(c.n); a.rule = c.rule; a.F = F;
+    a.st = c.st; a.plan = w.plan[h]; a.ROWS = w.ROWS[h]; a.COLS = nullptr; a.frow = w.frow; a.bvec = w.bvec;
+    a.rowlab = c.rowlab; a.collab = c.collab; a.trace = c.trace;
+    sa.ca.bv[0] = w.bvec; sa.ca.bv[1] = w.bvec2; sa.ca.cs = w.cs; sa.ca.part = w.part;
+    sa.rank = c.rank; sa.R = c.R; sa.col0 = c.col0; sa.seq = c.seq;
+    sa.prev_plan = with_prev ? w.plan[h ^ 1] : nullptr;
+    sa.prev_ROWS = with_prev ? w.ROWS[h ^ 1] : nullptr;
+    for (int g = 0; g < XB_MAX_RANKS; ++g) sa.xbox[g] = g < c.R ? static_cast<unsigned char *>(c.xbox[g]) : nullptr;
     if (g_shard_ctas < 0) {
         int dev = 0, coop = 0, per_sm = 0;
         cudaGetDevice(&dev);
@@ -964,29 +1028,100 @@ cudaError_t fused_shard_pass(double *A0, double *A1, double *b0, double *b1, int
             g_shard_ctas = min(COOP_MAX_CTAS, sm_count());
     }
     if (g_shard_ctas <= 0) return cudaErrorNotSupported;
-    int G = (max(n + 1, (int)ld) + COOP_THREADS - 1) / COOP_THREADS;
+    int G = (max(c.n + 1, (int)c.ld) + COOP_THREADS - 1) / COOP_THREADS;
     G = G > g_shard_ctas ? g_shard_ctas : (G < 1 ? 1 : G);
     void *args[] = {&sa};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)shard_price_kernel, dim3(G), dim3(COOP_THREADS), args, 0, stream);
-    if (e != cudaSuccess) return e;
-    spx_host::count_launch();
+    if (e == cudaSuccess) spx_host::count_launch();
+    return e;
+}
+
+static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, int h, int minb, cudaStream_t stream) {
     static bool configured = false;
+    cudaError_t e;
     if (!configured) {
         if ((e = cudaFuncSetAttribute(update_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(update_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
         configured = true;
     }
-    const XBoxLayout XL = xbox_layout(cbd, R);
-    const double *COLS = reinterpret_cast<const double *>(static_cast<unsigned char *>(xboxes[rank]) + XL.cols_off) +
-                         (int64_t)(seq & 1ull) * FUSE_MAX * R * cbd;
-    dim3 grid((unsigned)((m_loc + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + FUP_TR - 1) / FUP_TR));
+    const int64_t cbd = colbuf_doubles(c.n);
+    const XBoxLayout XL = xbox_layout(cbd, c.R);
+    const double *COLS = reinterpret_cast<const double *>(static_cast<unsigned char *>(c.xbox[c.rank]) + XL.cols_off) +
+                         (int64_t)h * FUSE_MAX * c.R * cbd;
+    dim3 grid((unsigned)((c.m_loc + FUP_TC - 1) / FUP_TC), (unsigned)((c.n + 1 + FUP_TR - 1) / FUP_TR));
     if (grid.x == 0) return cudaSuccess;                     // a shard without columns only prices
     if (minb == 3)
-        update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m_loc, ld, cbd, col0, R, plan, ROWS, COLS);
+        update_fused_kernel<3><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(c.A[0], c.A[1], c.n, c.m_loc, c.ld, cbd, c.col0,
+                                                                                c.R, w.plan[h], w.ROWS[h], COLS);
     else
-        update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(A0, A1, n, m_loc, ld, cbd, col0, R, plan, ROWS, COLS);
+        update_fused_kernel<4><<<grid, FUP_THREADS, sizeof(FusedSmem), stream>>>(c.A[0], c.A[1], c.n, c.m_loc, c.ld, cbd, c.col0,
+                                                                                c.R, w.plan[h], w.ROWS[h], COLS);
     spx_host::count_launch();
     return cudaGetLastError();
+}
+
+// Enqueue `pivots` pivots as passes of `depth` (the last one shorter).
+//   lookahead == false : price q, update q, price q+1, ... on `s`.
+//   lookahead == true  : the pricing of pass q+1 runs on the side stream WHILE the update of pass q streams
+//       on `s`; it gathers from the table the running update reads and replays that pass's levels first
+//       (up to 2 x depth - 1 pending levels).  P_q waits for U_{q-2} (its table and its buffer set),
+//       U_q waits for P_q.
+cudaError_t fused_run(FusedCtx &c, int64_t pivots, int depth, int minb, bool lookahead, cudaStream_t s) {
+    if (depth < 1) depth = 1;
+    if (depth > FUSE_MAX) depth = FUSE_MAX;
+    const FusedWork w = carve_work(c.work, c.n, c.ld);
+    cudaError_t e;
+    if (lookahead) {
+        if ((e = cudaEventRecord(c.ev_start, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(c.side, c.ev_start, 0)) != cudaSuccess) return e;
+    }
+    int64_t left = pivots;
+    for (int q = 0; left > 0; ++q) {
+        const int F = (int)(left < depth ? left : depth);
+        const int h = (int)(++c.seq & 1ull);
+        if (lookahead) {
+            if (q >= 2 && (e = cudaStreamWaitEvent(c.side, c.ev_upd[h], 0)) != cudaSuccess) return e;
+            if ((e = launch_shard_price(c, w, F, h, q > 0, c.side)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(c.ev_priced[h], c.side)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(s, c.ev_priced[h], 0)) != cudaSuccess) return e;
+            if ((e = launch_fused_update(c, w, h, minb, s)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(c.ev_upd[h], s)) != cudaSuccess) return e;
+        } else {
+            if ((e = launch_shard_price(c, w, F, h, false, s)) != cudaSuccess) return e;
+            if ((e = launch_fused_update(c, w, h, minb, s)) != cudaSuccess) return e;
+        }
+        left -= F;
+    }
+    return cudaSuccess;
+}
+
+// spx_solve's fused loop on ONE GPU: the sharded machinery with a single rank whose XBOX lives in the
+// caller's workspace; one cached side stream + event set per device
+static FusedCtx g_solo[64];
+
+cudaError_t fused_solve_passes(double *A0, double *A1, double *b0, double *b1, int n, int m, int64_t ld, int rule,
+                               spx_state *st, void *work, int32_t *rowlab, int32_t *collab, int32_t *trace,
+                               int64_t pivots, int depth, int minb, bool lookahead, cudaStream_t s) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    FusedCtx &c = g_solo[dev];
+    if (!c.side && (e = fused_ctx_streams(c)) != cudaSuccess) return e;
+    c.A[0] = A0; c.A[1] = A1; c.b[0] = b0; c.b[1] = b1;
+    c.n = n; c.m_loc = m; c.rule = rule; c.rank = 0; c.R = 1; c.ld = ld; c.col0 = 0;
+    c.st = st; c.work = work; c.rowlab = rowlab; c.collab = collab; c.trace = trace;
+    c.xbox[0] = carve_work(work, n, ld).xbox1;
+    return fused_run(c, pivots, depth, minb, lookahead, s);
+}
+
+// the caller must not free or reuse a workspace while side-stream work on it may be pending
+cudaError_t fused_solo_sync() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && g_solo[dev].side) return cudaStreamSynchronize(g_solo[dev].side);
+    return cudaSuccess;
 }
 
 int64_t xbox_bytes(int n, int R) { return xbox_layout(colbuf_doubles(n), R).bytes; }
@@ -996,14 +1131,8 @@ int xbox_max_ranks() { return XB_MAX_RANKS; }
 
 // ---- C ABI of the column-sharded fused loop (declared in include/spx_b200.h) -------------------
 struct spx_fshard {
-    int rank, R, n, m_loc, rule;
-    int64_t ld, col0;
-    double *A[2], *b[2];
-    spx_state *st;
-    void *work;
-    int32_t *rowlab, *collab, *trace;
-    void *xbox[16];
-    unsigned long long seq;
+    spx_launch::FusedCtx c;
+    bool lookahead;
 };
 
 extern "C" {
@@ -1028,15 +1157,25 @@ int spx_fshard_open(spx_fshard **out, int32_t rank, int32_t nranks, int32_t n, i
     }
     spx_fshard *h = new (std::nothrow) spx_fshard();
     if (!h) { set_error("spx_fshard_open: out of host memory"); return -2; }
-    h->rank = rank; h->R = nranks; h->n = n; h->m_loc = m_loc; h->rule = rule; h->ld = ld_loc; h->col0 = col0;
-    h->A[0] = d_A0; h->A[1] = d_A1; h->b[0] = d_b0; h->b[1] = d_b1;
-    h->st = d_state; h->work = d_work; h->rowlab = d_rowlab; h->collab = d_collab; h->trace = d_trace;
+    spx_launch::FusedCtx &c = h->c;
+    c.rank = rank; c.R = nranks; c.n = n; c.m_loc = m_loc; c.rule = rule; c.ld = ld_loc; c.col0 = col0;
+    c.A[0] = d_A0; c.A[1] = d_A1; c.b[0] = d_b0; c.b[1] = d_b1;
+    c.st = d_state; c.work = d_work; c.rowlab = d_rowlab; c.collab = d_collab; c.trace = d_trace;
     for (int g = 0; g < nranks; ++g) {
         if (!xboxes[g]) { delete h; set_error("spx_fshard_open: null xbox %d", g); return -2; }
-        h->xbox[g] = xboxes[g];
+        c.xbox[g] = xboxes[g];
     }
-    h->seq = 0;
+    c.seq = 0;
+    c.side = nullptr;
+    h->lookahead = true;
+    if (spx_host::check(spx_launch::fused_ctx_streams(c), "side stream")) { delete h; return -1; }
     *out = h;
+    return 0;
+}
+
+int spx_fshard_set_lookahead(spx_fshard *h, int32_t on) {
+    if (!h) return -2;
+    h->lookahead = on != 0;
     return 0;
 }
 
@@ -1045,30 +1184,24 @@ int spx_fshard_open(spx_fshard **out, int32_t rank, int32_t nranks, int32_t n, i
 int spx_fshard_enqueue(spx_fshard *h, int64_t pivots, int32_t depth, void *stream) {
     if (!h || pivots < 0) { spx_host::set_error("spx_fshard_enqueue: bad arguments"); return -2; }
     if (depth <= 0) depth = 8;
-    if (depth > spx_launch::fuse_max()) depth = spx_launch::fuse_max();
-    int64_t left = pivots;
-    while (left > 0) {
-        const int F = (int)(left < depth ? left : depth);
-        if (spx_host::check(spx_launch::fused_shard_pass(h->A[0], h->A[1], h->b[0], h->b[1], h->n, h->m_loc, h->ld, h->col0,
-                                                         h->rule, F, 0, h->st, h->work, h->rowlab, h->collab, h->trace,
-                                                         h->rank, h->R, ++h->seq, h->xbox,
-                                                         reinterpret_cast<cudaStream_t>(stream)), "fused shard pass"))
-            return -1;
-        left -= F;
-    }
-    return 0;
+    return spx_host::check(spx_launch::fused_run(h->c, pivots, depth, 0, h->lookahead,
+                                                 reinterpret_cast<cudaStream_t>(stream)), "fused shard passes");
 }
 
 int spx_fshard_read(spx_fshard *h, spx_state *h_state, int32_t *cur_buffer, void *stream) {
     if (!h || !h_state) { spx_host::set_error("spx_fshard_read: bad arguments"); return -2; }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (spx_host::check(cudaMemcpyAsync(h_state, h->st, sizeof(spx_state), cudaMemcpyDeviceToHost, s), "read state")) return -1;
+    if (spx_host::check(cudaStreamSynchronize(s), "sync")) return -1;
+    if (spx_host::check(cudaStreamSynchronize(h->c.side), "sync side")) return -1;
+    if (spx_host::check(cudaMemcpyAsync(h_state, h->c.st, sizeof(spx_state), cudaMemcpyDeviceToHost, s), "read state")) return -1;
     if (spx_host::check(cudaStreamSynchronize(s), "sync")) return -1;
     if (cur_buffer) *cur_buffer = (int32_t)(h_state->reserved[0] & 1);
     return 0;
 }
 
 int spx_fshard_close(spx_fshard *h) {
+    if (!h) return 0;
+    spx_launch::fused_ctx_destroy(h->c);
     delete h;
     return 0;
 }

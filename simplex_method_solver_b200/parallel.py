@@ -426,11 +426,12 @@ class FusedShardedTableau(ShardedTableau):
     own columns ONCE for all of them.  Same pivots and bits as every other loop."""
 
     def __init__(self, n: int, m: int, rank: int, world: int, device, trace_capacity: int = 0,
-                 group=None, rule: int = N.RULE_REFERENCE, depth: int = 8):
+                 group=None, rule: int = N.RULE_REFERENCE, depth: int = 8, lookahead: bool = True):
         super().__init__(n, m, rank, world, device, trace_capacity=trace_capacity, group=group, rule=rule,
                          lookahead=False)
         L = N.lib()
         self.depth = int(depth)
+        self.price_ahead = bool(lookahead)
         dev = self.device
         wbytes = int(L.spx_fused_workspace_bytes(self.n, max(self.m_loc, 1)))
         self.work = torch.zeros(wbytes // 8 + 16, dtype=torch.float64, device=dev)
@@ -441,6 +442,7 @@ class FusedShardedTableau(ShardedTableau):
                    rule, self.A[0].data_ptr(), self.A[1].data_ptr(), self.b[0].data_ptr(), self.b[1].data_ptr(),
                    self.state.data_ptr(), self.work.data_ptr(), self.work.numel() * 8, self.rowlab.data_ptr(),
                    self.collab.data_ptr(), N.ptr(self.trace), self.xbox.ptrs)
+            N.call("spx_fshard_set_lookahead", self.handle, int(self.price_ahead))
         self._cur = 0
 
     def load(self, rows, function, max_pivots: int):

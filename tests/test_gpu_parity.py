@@ -510,9 +510,36 @@ def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookah
             bx.close()
 
 
+@pytest.mark.parametrize("pricing", [1, 2])
+@pytest.mark.parametrize("n,m,depth", [(7, 15, 3), (64, 512, 8), (130, 1030, 5), (40, 2049, 8)])
+def test_fused_pass_entry_point_both_pricing_kernels(spx, n, m, depth, pricing):
+    """spx_fused_pass (the stand-alone pass bench.py times): one-CTA and whole-GPU cooperative pricing."""
+    L = spx.N.lib()
+    rows, c = W.dense_lp(n, m, seed=n + m)
+    o = oracle.solve(rows, c, max_pivots=4 * depth)
+    dev = spx.engine.DeviceTableau(n, m, trace_capacity=64)
+    dev.load(rows, c, max_pivots=4 * depth)
+    try:
+        assert L.spx_set_option(8, pricing) == 0
+        for _ in range(5):                                   # one pass more than the cap allows
+            dev.fused_pass(depth, 0)
+    finally:
+        L.spx_set_option(8, 0)
+    st = dev.read_state()
+    assert (st.status, st.npiv) == (o.status, o.npiv)
+    assert dev.trace[: st.npiv].cpu().numpy().tolist() == o.trace.tolist()
+    cur = int(st.reserved[0]) & 1
+    body = dev.A[cur, :, :m].cpu().numpy()
+    ob = np.zeros((n + 1, m))
+    ob[:n] = o.table[: n * (m + 1)].reshape(n, m + 1)[:, :m]
+    ob[n] = o.table[n * (m + 1):]
+    assert np.array_equal(bits(body), bits(ob))
+
+
 @pytest.mark.parametrize("n,m,kind,depth", [(20, 700, "dense", 8), (33, 2500, "dense", 3), (12, 1300, "smallint", 8),
                                             (9, 40, "smallint", 5), (300, 700, "dense", 8)])
-def test_fused_sharded_loop_single_rank(spx, n, m, kind, depth):
+@pytest.mark.parametrize("ahead", [True, False])
+def test_fused_sharded_loop_single_rank(spx, n, m, kind, depth, ahead):
     """The column-sharded fused loop (cooperative pricing with the in-kernel exchange) with ONE rank:
     the whole code path except the cross-rank selection, against the oracle."""
     from simplex_method_solver_b200 import parallel as P
@@ -524,7 +551,7 @@ def test_fused_sharded_loop_single_rank(spx, n, m, kind, depth):
         c = rng.integers(-3, 4, m).astype(float)
     cap = 45
     o = oracle.solve(rows, c, max_pivots=cap)
-    sh = P.FusedShardedTableau(n, m, 0, 1, "cuda", trace_capacity=cap + 16, depth=depth)
+    sh = P.FusedShardedTableau(n, m, 0, 1, "cuda", trace_capacity=cap + 16, depth=depth, lookahead=ahead)
     try:
         sh.load(rows, c, max_pivots=cap)
         status, npiv = sh.solve(cap, check_every=7)
