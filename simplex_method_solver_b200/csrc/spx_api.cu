@@ -369,8 +369,10 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
             int F = (int)spx_launch::get_option(SPX_OPT_FUSE_DEPTH);
             if (F <= 0) F = 8;
             if (F > spx_launch::fuse_max()) F = spx_launch::fuse_max();
-            // look-ahead (default): the pricing of pass q+1 runs on a side stream during the update of pass q
-            const bool la = spx_launch::get_option(SPX_OPT_FUSE_LOOKAHEAD) != 2;
+            // look-ahead (option): the pricing of pass q+1 runs on a side stream during the update of pass q.
+            // Off by default on ONE GPU: pricing is 4 % of a pass there and the overlap costs as much as it
+            // hides (measured 3.14 k vs 3.21 k pivots/s); on by default in the column-sharded loop.
+            const bool la = spx_launch::get_option(SPX_OPT_FUSE_LOOKAHEAD) == 1;
             if (check(spx_launch::fused_solve_passes(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, d_state, d_work, d_rowlab,
                                                      d_collab, d_trace, k, F,
                                                      (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS), la, s),

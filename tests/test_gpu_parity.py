@@ -15,23 +15,23 @@ pytestmark = pytest.mark.gpu
 
 
 class loop_mode:
-    """'fused-coop' = the fused loop with the whole-GPU cooperative pricing kernel forced on (small
-    tableaus would pick the one-CTA pricing kernel); every other name passes through."""
+    """'fused-coop' = the fused loop of spx_solve with look-ahead pricing (side stream, replay through the
+    previous pass's pending levels) switched on; every other name passes through."""
 
     def __init__(self, name):
         self.name = name
 
     def __enter__(self):
-        if self.name == "fused-coop":
+        if self.name == "fused-coop":                  # here: the fused loop of spx_solve with look-ahead pricing on
             from simplex_method_solver_b200 import _native as N
-            assert N.lib().spx_set_option(8, 2) == 0
+            assert N.lib().spx_set_option(9, 1) == 0
             return "fused"
         return self.name
 
     def __exit__(self, *a):
         if self.name == "fused-coop":
             from simplex_method_solver_b200 import _native as N
-            N.lib().spx_set_option(8, 0)
+            N.lib().spx_set_option(9, 0)
 
 
 @pytest.fixture(scope="module")
