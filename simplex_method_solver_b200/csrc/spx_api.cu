@@ -373,10 +373,22 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
             // Off by default on ONE GPU: pricing is 4 % of a pass there and the overlap costs as much as it
             // hides (measured 3.14 k vs 3.21 k pivots/s); on by default in the column-sharded loop.
             const bool la = spx_launch::get_option(SPX_OPT_FUSE_LOOKAHEAD) == 1;
-            if (check(spx_launch::fused_solve_passes(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, d_state, d_work, d_rowlab,
-                                                     d_collab, d_trace, k, F,
-                                                     (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS), la, s),
-                      "fused pass launch")) return -1;
+            if (la) {
+                if (check(spx_launch::fused_solve_passes(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, d_state, d_work, d_rowlab,
+                                                         d_collab, d_trace, k, F,
+                                                         (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS), true, s),
+                          "fused pass launch")) return -1;
+            } else {
+                int64_t left = k;
+                while (left > 0) {
+                    const int Fp = (int)(left < F ? left : F);
+                    if (check(spx_launch::fused_pass(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, Fp,
+                                                     (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS),
+                                                     (int)spx_launch::get_option(SPX_OPT_FUSE_PRICING), 0, d_state, d_work,
+                                                     d_rowlab, d_collab, d_trace, s), "fused pass launch")) return -1;
+                    left -= Fp;
+                }
+            }
             if (check(cudaMemcpyAsync(&hs, d_state, sizeof(hs), cudaMemcpyDeviceToHost, s), "read state")) return -1;
             if (check(cudaStreamSynchronize(s), "fused passes")) return -1;
             if (check(spx_launch::fused_solo_sync(), "fused side stream")) return -1;

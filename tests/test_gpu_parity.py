@@ -22,16 +22,21 @@ class loop_mode:
         self.name = name
 
     def __enter__(self):
-        if self.name == "fused-coop":                  # here: the fused loop of spx_solve with look-ahead pricing on
-            from simplex_method_solver_b200 import _native as N
+        from simplex_method_solver_b200 import _native as N
+        if self.name == "fused-coop":                  # the fused loop of spx_solve with look-ahead pricing on
             assert N.lib().spx_set_option(9, 1) == 0
+            return "fused"
+        if self.name == "fused-gpuwide":               # ... with the whole-GPU cooperative pricing kernel forced on
+            assert N.lib().spx_set_option(8, 2) == 0
             return "fused"
         return self.name
 
     def __exit__(self, *a):
+        from simplex_method_solver_b200 import _native as N
         if self.name == "fused-coop":
-            from simplex_method_solver_b200 import _native as N
             N.lib().spx_set_option(9, 0)
+        if self.name == "fused-gpuwide":
+            N.lib().spx_set_option(8, 0)
 
 
 @pytest.fixture(scope="module")
@@ -120,7 +125,7 @@ def test_problem_files_feed_the_batched_solver(spx):
 
 # --------------------------------------------------------------------------- all golden cases
 @pytest.mark.parametrize("lookahead,chunk", [(False, 7), (True, 7), (True, 4), (True, 1), ("resident", 7), (None, 5),
-                                             ("fused", 7), ("fused", 3), ("fused-coop", 7)])
+                                             ("fused", 7), ("fused", 3), ("fused-coop", 7), ("fused-gpuwide", 5)])
 def test_all_reference_cases_streaming_solver(spx, ref_cases, lookahead, chunk):
     """solve(): device-side loop, classic (pick k, update k, ...) and look-ahead (pivot k+1 priced
     from table k on a side stream while update k runs); trace, ending, labels, final table bits."""
@@ -280,7 +285,7 @@ def test_pick_update_bit_exact_ragged_shapes(spx, n, m):
         assert dev.read_state().npiv == npiv
 
 
-@pytest.mark.parametrize("mode", ["resident", "fused", "fused-coop"])
+@pytest.mark.parametrize("mode", ["resident", "fused", "fused-coop", "fused-gpuwide"])
 @pytest.mark.parametrize("n,m", [(1, 2), (3, 1), (7, 15), (9, 17), (64, 512), (65, 513), (130, 1030), (257, 100), (40, 2049)])
 def test_resident_and_fused_loops_bit_exact_ragged_shapes(spx, n, m, mode):
     with loop_mode(mode) as mode_:
