@@ -5,18 +5,23 @@
 
 Workload (config.workload): cfg4 of BASELINE.json — the dense 16384 x 32768 fp64 LP
 D(16384, 32768, seed 0) of SURVEY.md §8d.  One *step* = PIVOTS_PER_STEP (1000) consecutive
-pivots (pick + rank-1 update) of that tableau.  The full solve needs ~1e6 pivots, so
-timed steps simply continue the same solve; the pivot sequence of the run is checked
-against the golden prefix (tests/golden/cfg_digests.json) before anything is printed.
+pivots of that tableau.  The full solve needs ~1e6 pivots, so timed steps simply continue the same
+solve; the pivot sequence of the run is checked against the 2000-pivot golden prefix
+(tests/golden/cfg_digests.json) before anything is printed.
 
-  value   pivots/s with the tableau resident in HBM (CUDA events, max over ranks)
+  value   pivots/s with the tableau resident in HBM (CUDA events, max over ranks); the loop is the fused
+          one: 8 pivots priced from the stored table, then ONE stream over the body applies them all
   e2e     pivots/s through the public API (SimplexMethod(rows, c).solve(...)) with the
           4.3 GB tableau in PINNED HOST memory: upload + pivots + result read-back
-  roofline  the update kernel alone: 16 B x cells per launch / its CUDA-event duration
+  roofline  the dominant kernel (update_fused_kernel): 16 B x cells per LAUNCH / its CUDA-event duration, plus
+          its fp64-issue fraction; roofline_single_pivot_kernel: the one-pivot-per-pass streaming kernel
+          (16 B x cells per pivot — the north star's roofline)
   cpu_baseline  oracle/spx_oracle.c (a C port of the reference's loop, OpenMP) on this host
+  batched / l2_resident  the other BASELINE configs that fit one line: cfg3 (65,536 small LPs) and cfg2 (1000 x 2000)
 
-N > 1 (torchrun): the body is column-sharded, one process per GPU, one all-gather of
-{key, candidate column} per pivot over NCCL (strong scaling: the tableau is fixed).
+N > 1 (torchrun): the body is column-sharded, one process per GPU; per pivot the ranks exchange their entering
+keys and candidate columns over NVLink peer memory from inside the pricing kernel (strong scaling: the tableau is
+fixed); the cfg3 batch is split over the ranks with no collective.
 --impl reference: the reference's algorithm on the host cores (the oracle port; the
 reference itself is pure Python and cannot travel to the GPU box), same config.
 """
@@ -310,6 +315,11 @@ def resident_leg(dev):
             "parity": "13,579 pivots, sha256 of the pivot sequence == golden"}
 
 
+def fused_depth_for(world: int) -> int:
+    """Pivots per pass of the sharded fused loop: 8 everywhere (measured; see profiles/README.md)."""
+    return 8
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -491,7 +501,8 @@ def run_ours(args):
     if args.exchange == "fused":
         # passes of 8 pivots: cooperative pricing with the in-kernel NVLink exchange, then ONE stream
         # over the local columns applies them all (csrc/spx_fused.cu)
-        sh = FusedShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
+        sh = FusedShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
+                                 depth=args.depth or fused_depth_for(world))
     elif args.exchange == "p2p":
         # C-side look-ahead loop, candidates exchanged by NVLink peer stores (csrc/spx_shard.cu)
         sh = PeerShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
@@ -559,6 +570,7 @@ def main():
     ap.add_argument("--ref-pivots-per-step", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the cfg3 batched-LP leg")
+    ap.add_argument("--depth", type=int, default=0, help="N>1 fused loop: pivots per pass (0 = default)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "p2p", "nccl"],
                     help="N>1: fused passes with the in-kernel NVLink exchange (default); pivot-at-a-time look-ahead "
                          "with NVLink peer mailboxes (p2p) or an NCCL all-gather (nccl)")
