@@ -510,7 +510,6 @@ def run_ours(args):
         sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
                             lookahead=not args.no_lookahead)
     sh.load(rows, c, max_pivots=need + 64)
-    del rows
     for _ in range(args.warmup):
         sh.run(P)
     torch.cuda.synchronize()
@@ -537,18 +536,48 @@ def run_ours(args):
     assert (tr[:k] == gold[:k]).all(), "sharded pivot sequence differs from the golden prefix"
     value = args.steps * P / (total_ms * 1e-3)
     alg_bytes = 16.0 * cells(N_ROWS, M_COLS)
-    if args.exchange in ("p2p", "fused"):
-        sh.close()
-    del sh
-    torch.cuda.empty_cache()
-    batched = batched_leg(dev, rank, world, dist) if not args.no_batched else None
+
+    # ---------------- e2e at N GPUs: every rank uploads ITS column block from pinned host memory, the
+    # ranks pivot together, every rank reads its state and trace back; wall clock between barriers, max over ranks
+    e2e = None
+    if args.exchange == "fused":
+        blk = torch.empty((N_ROWS, sh.m_loc + 1), dtype=torch.float64).pin_memory()
+        blk.numpy()[:, : sh.m_loc] = rows[:, sh.col0: sh.col0 + sh.m_loc]
+        blk.numpy()[:, sh.m_loc] = rows[:, M_COLS]
+        cblk = np.ascontiguousarray(c[sh.col0: sh.col0 + sh.m_loc])
+        e2e_steps = max(1, min(args.steps, 3))
+        ts = []
+        for it in range(1 + e2e_steps):                     # first iteration is a warm-up
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            sh.load_local(blk.numpy(), cblk, max_pivots=P + 64)
+            sh.run(P)
+            st2 = sh.sync()
+            tr2 = sh.trace[:P].cpu().numpy()
+            torch.cuda.synchronize()
+            dist.barrier()
+            dt = time.perf_counter() - t0
+            assert st2.npiv == P and (tr2 == gold[:P]).all(), "e2e: sharded pivot sequence differs from the golden prefix"
+            if it > 0:
+                ts.append(dt)
+        tmax = torch.tensor([statistics.mean(ts)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e = {"value": P / float(tmax.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(8 * (N_ROWS * (M_COLS + world) + M_COLS)),
+               "d2h_bytes_per_step": int(world * (tr2.nbytes + 128)), "steps": e2e_steps,
+               "ms_per_step": 1e3 * float(tmax.item()),
+               "api": f"FusedShardedTableau.load_local(pinned_block, c_block); run({P}); sync() on every rank"}
+        del blk
+    del rows
+    if args.exchange in ("p2p", "fused"):    batched = batched_leg(dev, rank, world, dist) if not args.no_batched else None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(world), "clocks": clk.summary(),
-            "e2e": None, "gpu_launches": launches,
+            "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "update_kernel (K3), whole step incl. exchange",
                          "achieved": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9 / world,
                          "peak": peak, "unit": "GB/s per GPU", "peak_source": peak_src,

@@ -229,6 +229,17 @@ class ShardedTableau:
         self.npiv_enqueued = 0
         self.si, self.priced = 0, False
 
+    def load_local(self, block: np.ndarray, function_block: np.ndarray, max_pivots: int):
+        """Upload this rank's OWN packed block: `block` is [n, m_loc + 1] = this rank's columns followed by
+        the b column (e.g. a view of pinned host memory), `function_block` its m_loc objective entries."""
+        assert block.shape == (self.n, self.m_loc + 1) and block.dtype == np.float64 and block.flags.c_contiguous
+        fb = np.ascontiguousarray(function_block, dtype=np.float64)
+        assert fb.shape == (self.m_loc,)
+        self.ops.import_shard(block, fb, self.A[0], self.b[0], self.n, max(self.m_loc, 1), 0, self.m_loc, self.ld)
+        self.ops.init_state(self.state, self.rowlab, self.collab, self.n, self.m, int(max_pivots))
+        self.npiv_enqueued = 0
+        self.si, self.priced = 0, False
+
     def _all_gather(self):
         if self.world > 1:
             dist.all_gather_into_tensor(self.gathered.view(-1), self.send, group=self.group)
@@ -447,6 +458,10 @@ class FusedShardedTableau(ShardedTableau):
 
     def load(self, rows, function, max_pivots: int):
         super().load(rows, function, max_pivots)       # init_state leaves reserved[0] = 0: table 0 in buffer 0
+        self._cur = 0
+
+    def load_local(self, block, function_block, max_pivots: int):
+        super().load_local(block, function_block, max_pivots)
         self._cur = 0
 
     def step(self):
