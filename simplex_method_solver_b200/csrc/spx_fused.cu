@@ -432,14 +432,13 @@ coop_price_kernel(CoopArgs ca) {
 constexpr int XB_MAX_RANKS = 16;
 
 struct XBoxLayout {
-    int64_t cols_off, keys_off, kflag_off, cflag_off, bytes;
+    int64_t cols_off, keys_off, kflag_off, bytes;
 };
 __host__ __device__ inline XBoxLayout xbox_layout(int64_t cbd, int R) {
     XBoxLayout L;
     L.cols_off = 0;
     L.keys_off = (2LL * FUSE_MAX * R * cbd * 8 + 127) / 128 * 128;
     L.kflag_off = L.keys_off + ((int64_t)(FUSE_MAX + 1) * 2 * R * 16 + 127) / 128 * 128;
-    L.cflag_off = 0;
     L.bytes = L.kflag_off + ((int64_t)(FUSE_MAX + 1) * 2 * R * 8 + 127) / 128 * 128;
     return L;
 }

@@ -58,7 +58,7 @@ def _worker(rank, world, port, n, m, seed, cap, mode, out):
 
 
 @pytest.mark.parametrize("mode", ["fused", "p2p", "nccl", "nccl-ahead"])
-@pytest.mark.parametrize("n,m,cap", [(300, 2600, 150), (64, 1024, 400)])
+@pytest.mark.parametrize("n,m,cap", [(300, 2600, 150), (64, 1024, 400), (9, 40, 60)])   # last: ranks >= 1 own no columns
 def test_sharded_flow_on_real_gpus(mode, n, m, cap):
     import torch
     import torch.multiprocessing as mp
