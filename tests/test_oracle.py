@@ -191,3 +191,53 @@ def test_golden_file_provenance(ref_cases):
     assert all(c.get("provenance") == "reference" for c in ref_cases)
     h = hashlib.sha256(repr(sorted(names)).encode()).hexdigest()
     assert len(h) == 64
+
+
+# --------------------------------------------------------------------------- the idea behind the fused loop (K6)
+def test_lazy_replay_of_pending_pivots_is_bit_identical():
+    """csrc/spx_fused.cu prices the next F pivots from the STORED table by replaying the pending rank-1
+    updates on single cells.  CPU model of that claim: any cell of the table after i pivots, evaluated
+    lazily from table 0 with the reference's operation order (simplex.py:156,160,163,173-175), equals the
+    materialised cell bit for bit — for pivot rows, pivot columns, pivot cells and ordinary cells alike."""
+    rng = np.random.default_rng(21)
+    for trial in range(12):
+        n, m = int(rng.integers(2, 9)), int(rng.integers(2, 8))
+        if trial % 2:
+            rows = np.hstack([rng.integers(-3, 4, (n, m)).astype(float), rng.integers(0, 7, (n, 1)).astype(float)])
+            c = rng.integers(-3, 1, m).astype(float)
+        else:
+            rows, c = W.dense_lp(n, m, seed=trial)
+        T = flat_of(rows, c)
+        w1 = m + 1
+        levels, tables = [], [T.copy()]
+        for _ in range(6):
+            st, r, cc, p = oracle.pick(T, n, m)
+            if st != oracle.PIVOT:
+                break
+            row = T[r * w1: r * w1 + m].copy()                                   # ROW_i: pivot row of table i
+            col = np.array([T[i * w1 + cc] for i in range(n)] + [T[n * w1 + cc]])   # COL_i (f row last)
+            levels.append((r, cc, p, row, col))
+            T = oracle.update(T, n, m, r, cc)
+            tables.append(T.copy())
+
+        def lazy(t, j, upto):
+            """cell (t, j) of table `upto`, from table 0 (t == n: the f row)."""
+            v = tables[0][t * w1 + j] if t < n else tables[0][n * w1 + j]
+            for (r, cc, p, row, col) in levels[:upto]:
+                with np.errstate(all="ignore"):
+                    if t == r:
+                        v = np.float64(1.0) / p if j == cc else (-v) / p
+                    elif j == cc:
+                        v = col[t] / p
+                    else:
+                        v = (v * p - row[j] * col[t]) / p
+            return np.float64(v)
+
+        for upto in range(1, len(levels) + 1):
+            Tm = tables[upto]
+            for t in range(n + 1):
+                for j in range(m):
+                    want = Tm[t * w1 + j] if t < n else Tm[n * w1 + j]
+                    got = lazy(t, j, upto)
+                    assert bits(np.array([got]))[0] == bits(np.array([want]))[0] or (np.isnan(got) and np.isnan(want)), \
+                        (trial, upto, t, j, got, want)
