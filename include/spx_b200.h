@@ -76,7 +76,8 @@ typedef struct spx_state {
     int64_t hint_tag[2];
     int32_t hint_bneg[2]; /* first i with b[i] < 0, INT32_MAX none                      */
     int32_t hint_fneg[2]; /* first LOCAL j with f[j] < 0, INT32_MAX none                */
-    int64_t reserved[6];
+    int64_t reserved[6];  /* [0]: fused loops only — index (0/1) of the ping-pong buffer holding table npiv
+                           *      (they flip once per PASS, not per pivot); 0 elsewhere                   */
 } spx_state;
 
 /* ---- library ----------------------------------------------------------- */
@@ -96,10 +97,10 @@ int64_t     spx_launch_count(int reset);
 #define SPX_OPT_PIPE_ORDER       3  /* pipelined kernel tile order: 0 chunked column-major, 1 interleaved row-major */
 #define SPX_OPT_PIPE_GRID        4  /* pipelined kernel CTAs (0 = one per SM) */
 #define SPX_OPT_TILED_ROWS       5  /* tiled kernel rows per tile (0 = auto; else a multiple of 8 <= 64) */
-#define SPX_OPT_FUSE_LOOKAHEAD   9  /* fused loop in spx_solve: 1 = price pass q+1 on a side stream during update q (default 0: off on one GPU) */
-#define SPX_OPT_FUSE_PRICING     8  /* fused loop pricing kernel: 0 auto, 1 one CTA, 2 whole-GPU cooperative */
-#define SPX_OPT_FUSE_MIN_BLOCKS  7  /* fused update kernel: resident CTAs per SM its register budget targets (2..4, 0 = default) */
 #define SPX_OPT_FUSE_DEPTH       6  /* fused loop: pivots applied per pass over the body (0 = default 8, max 8) */
+#define SPX_OPT_FUSE_MIN_BLOCKS  7  /* fused update kernel: resident CTAs per SM its register budget targets (2..4, 0 = default 4) */
+#define SPX_OPT_FUSE_PRICING     8  /* fused loop pricing kernel: 0 auto, 1 one CTA, 2 whole-GPU cooperative */
+#define SPX_OPT_FUSE_LOOKAHEAD   9  /* fused loop in spx_solve: 1 = price pass q+1 on a side stream during update q (default 0: off on one GPU) */
 int         spx_set_option(int32_t option, int64_t value);
 int64_t     spx_get_option(int32_t option);
 /* Device self-test of the hoisted-reciprocal division used by K3 against the
