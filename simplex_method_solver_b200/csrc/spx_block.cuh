@@ -110,4 +110,15 @@ __device__ int block_first_index_fn(int len, Val val, Pred pred, Scratch &s) {
     return SPX_NONE;
 }
 
+// ---- lazy replay (fused loops): a pending pivot "level" applied to ONE cell ------------------
+// Level l = (r, c, p) with ROW_l = the pivot row and COL_l = the pivot column of the table the level
+// is applied to.  The cell (t, j) of the next table follows from its current value v, ROW_l[j] and
+// COL_l[t] with the reference's formulas and roundings (simplex.py:156, :160, :163, :173-175).
+struct LevelDiv { int r, c; PivotDiv d; };
+
+__device__ __forceinline__ double apply_level(double v, int t, int j, const LevelDiv &L, double row_j, double col_t) {
+    if (t == L.r) return (j == L.c) ? pivot_cell_update(L.d.p) : pivot_div(-v, L.d);      // :163, :156
+    return (j == L.c) ? pivot_div(col_t, L.d) : cell_update(v, L.d, row_j, col_t);         // :160, :173-175
+}
+
 } // namespace spx

@@ -49,14 +49,6 @@ struct alignas(128) PlanHeader {
     int32_t owner[FUSE_MAX];   // column-sharded: the rank whose plane holds COL_l (0 on one GPU)
 };
 
-struct LevelDiv { int r, c; PivotDiv d; };
-
-// one pending level applied to the cell (t, j) whose current value is v
-__device__ __forceinline__ double apply_level(double v, int t, int j, const LevelDiv &L, double row_j, double col_t) {
-    if (t == L.r) return (j == L.c) ? pivot_cell_update(L.d.p) : pivot_div(-v, L.d);      // :163, :156
-    return (j == L.c) ? pivot_div(col_t, L.d) : cell_update(v, L.d, row_j, col_t);         // :160, :173-175
-}
-
 struct PriceArgs {
     double *A[2];
     double *b[2];
