@@ -345,7 +345,12 @@ __global__ void division_selftest_kernel(const double *__restrict__ a, const dou
         const PivotDiv d = pivot_div_prepare(pv);
         const double q = pivot_div(a[k], d);
         const double e = __ddiv_rn(a[k], pv);
-        const bool same = (__double_as_longlong(q) == __double_as_longlong(e)) || (q != q && e != e);
+        // the fused kernel's form: guards accumulated, exact redo when one tripped
+        bool ok = true;
+        double q2 = pivot_div_unchecked(a[k], d, ok);
+        if (!ok) q2 = pivot_div(a[k], d);
+        const bool same = ((__double_as_longlong(q) == __double_as_longlong(e)) || (q != q && e != e)) &&
+                          ((__double_as_longlong(q2) == __double_as_longlong(e)) || (q2 != q2 && e != e));
         if (!same) {
             if (atomicAdd(mismatches, 1ull) == 0ull) { first_bad[0] = a[k]; first_bad[1] = pv; }
         }
