@@ -165,7 +165,7 @@ int spx_update(const double *d_Ain, double *d_Aout, const double *d_bin, double 
  * phase-1 row and the next entering column are O(n+m) cells computed with the update's own
  * arithmetic — so the update kernels run back to back and pricing is off the critical path.
  * Pivot sequence and every cell are identical in both modes. */
-#define SPX_LOOP_AUTO      0  /* resident if the tableau fits L2; fused (else look-ahead) if >= 256 MB and the workspace allows; else classic */
+#define SPX_LOOP_AUTO      0  /* resident if the tableau fits L2; fused if the body is >= 256 MB; else look-ahead (workspace permitting), else classic */
 #define SPX_LOOP_CLASSIC   1
 #define SPX_LOOP_LOOKAHEAD 2
 #define SPX_LOOP_RESIDENT  3  /* ONE persistent cooperative kernel runs the whole loop (n <= 4095, both bodies in L2):

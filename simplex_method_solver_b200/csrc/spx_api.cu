@@ -318,7 +318,9 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
         else if (d_work != nullptr && ((uintptr_t)d_work & 127) == 0 &&
                  work_bytes >= spx_launch::fused_workspace_bytes(n, ld) &&
                  (int64_t)(n + 1) * ld * 8 >= (256LL << 20)) mode = SPX_LOOP_FUSED;
-        else if (d_work != nullptr && (int64_t)(n + 1) * ld * 8 >= (256LL << 20)) mode = SPX_LOOP_LOOKAHEAD;
+        // in between (measured, tools/cfg2_lab.py 2000 4000: classic 32, fused 28, look-ahead 23 us/pivot)
+        else if (d_work != nullptr && ((uintptr_t)d_work & 127) == 0 && work_bytes >= workspace_bytes(n))
+            mode = SPX_LOOP_LOOKAHEAD;
         else mode = SPX_LOOP_CLASSIC;
     }
     SPX_REQUIRE(mode != SPX_LOOP_RESIDENT || spx_launch::resident_fits(n, m, ld),

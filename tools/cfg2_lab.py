@@ -15,7 +15,8 @@ from simplex_method_solver_b200.engine import DeviceTableau  # noqa: E402
 def main():
     n, m = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1000, 2000)
     rows, c = W.dense_lp(n, m, 0)
-    for mode in ("resident", "classic", "lookahead"):
+    modes = sys.argv[3].split(",") if len(sys.argv) > 3 else ["resident", "classic", "lookahead"]
+    for mode in modes:
         tab = DeviceTableau(n, m, trace_capacity=200000)
         tab.load(rows, c, max_pivots=200000)
         tab.solve(stop_after=50, lookahead=mode)
