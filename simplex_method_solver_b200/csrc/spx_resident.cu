@@ -4,8 +4,10 @@
 // recalculate_matrix() (:143-177) inside.
 //
 // A tableau that fits L2 is latency-bound, not HBM-bound: one pivot streams in ~4 us, so two
-// kernel launches per pivot (pick + update, ~25 us) dominate.  Here every SM keeps two CTAs
-// resident for the whole solve and a pivot costs ONE grid barrier:
+// kernel launches per pivot (pick + update, ~25 us) dominate.  Here every SM keeps one 512-thread CTA
+// resident for the whole solve (measured: 11.8 us/pivot at cfg2; two 256-thread CTAs per SM: 13.9 —
+// half as many redundant pricings hammer the same L2 lines and the barrier has half the arrivals)
+// and a pivot costs ONE grid barrier:
 //   - every CTA prices the pivot REDUNDANTLY (the decision depends on O(n + m) cells: its own
 //     shared-memory replica of the b column, one row scan and one column gather from L2), so all
 //     CTAs agree on (r, c, p) without exchanging anything;
@@ -25,8 +27,8 @@ namespace {
 
 using namespace spx;
 
-constexpr int RES_THREADS = 256;
-constexpr int RES_TC      = 2 * RES_THREADS;   // 512 columns per tile
+constexpr int RES_THREADS = 512;
+constexpr int RES_TC      = 2 * RES_THREADS;   // 1024 columns per tile
 constexpr int RES_PASS    = 16;                // rows a thread keeps in flight per pass
 constexpr int RES_MAX_N   = 4095;              // s_col + s_b must fit shared memory
 
@@ -45,7 +47,7 @@ struct ResidentArgs {
 __device__ __forceinline__ double2 ldcg2(const double *p) { return __ldcg(reinterpret_cast<const double2 *>(p)); }
 __device__ __forceinline__ void stcg2(double *p, double2 v) { __stcg(reinterpret_cast<double2 *>(p), v); }
 
-__global__ void __launch_bounds__(RES_THREADS, 2)
+__global__ void __launch_bounds__(RES_THREADS, 1)
 resident_loop_kernel(ResidentArgs a) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double res_smem[];
