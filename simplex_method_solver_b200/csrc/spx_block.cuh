@@ -33,6 +33,19 @@ __device__ __forceinline__ int block_min_int(int v, Scratch &s) {
     return out;
 }
 
+// two independent index minima in one pass over shared memory (one barrier pair instead of two
+// reductions): used where two first-index searches have no data dependence on each other
+__device__ __forceinline__ void block_min_int2(int &a, int &b, Scratch &s) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+    a = warp_min_int(a);
+    b = warp_min_int(b);
+    if (lane == 0) { s.red_i[warp] = a; s.red_k[warp] = (unsigned long long)(unsigned)b; }
+    __syncthreads();
+    a = warp_min_int(lane < nw ? s.red_i[lane] : SPX_NONE);
+    b = warp_min_int(lane < nw ? (int)(unsigned)s.red_k[lane] : SPX_NONE);
+    __syncthreads();                              // red_i / red_k may be reused right away
+}
+
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) {

@@ -73,31 +73,46 @@ resident_loop_kernel(ResidentArgs a) {
     for (;;) {
         const double *A = a.A[cur];
         double *An = a.A[cur ^ 1];
-        // ---------------- K1: phase-1 row from the replica of b, then the entering column (from L2)
-        const int rb = block_first_index_fn(n, [&](int i) { return s_b[i]; }, IsNeg(), s);
-        r1 = (rb == SPX_NONE) ? -1 : rb;
+        // ---------------- K1: phase-1 row from the replica of b and, in the same sweep and the same
+        // reduction, the first negative cell of the head of the f row (the two searches are independent;
+        // the f head is what :94-98 finds in all but degenerate tables)
+        const double *frow = A + (int64_t)n * ld;
+        const int head = min(m, 4 * nt);
+        int bneg = SPX_NONE, fneg = SPX_NONE;
+        {
+            double fv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int j = u * nt + tid; fv[u] = (j < head) ? __ldcg(frow + j) : 0.0; }
+            for (int i = tid; i < n; i += nt) if (s_b[i] < 0.0) { bneg = i; break; }
+#pragma unroll
+            for (int u = 3; u >= 0; --u) { const int j = u * nt + tid; if (j < head && fv[u] < 0.0) fneg = j; }
+        }
+        block_min_int2(bneg, fneg, s);
+        r1 = (bneg == SPX_NONE) ? -1 : bneg;
         if (r1 >= 0) {
             const double *row = A + (int64_t)r1 * ld;
             cl = block_first_index_fn(m, [&](int j) { return __ldcg(row + j); }, IsPos(), s);      // :82-85
-        } else {
-            const double *f = A + (int64_t)n * ld;
-            if (a.rule == SPX_RULE_REFERENCE) {
-                cl = block_first_index_fn(m, [&](int j) { return __ldcg(f + j); }, IsNeg(), s);    // :94-98
-            } else {                                  // Dantzig: most negative, lowest index on ties
-                unsigned long long best = ~0ull;
+        } else if (a.rule == SPX_RULE_REFERENCE) {
+            cl = fneg;                                                                              // :94-98
+            if (cl == SPX_NONE && m > head) {            // nothing in the head: scan the rest of the f row
+                const int rest = block_first_index_fn(m - head, [&](int j) { return __ldcg(frow + head + j); }, IsNeg(), s);
+                cl = (rest == SPX_NONE) ? SPX_NONE : head + rest;
+            }
+        } else {                                          // Dantzig: most negative, lowest index on ties
+            const double *f = frow;
+            unsigned long long best = ~0ull;
+            for (int j = tid; j < m; j += nt) {
+                const double v = __ldcg(f + j);
+                if (v < 0.0) { const unsigned long long k = orderable(v); best = k < best ? k : best; }
+            }
+            best = block_min_u64(best, s);
+            int loc = SPX_NONE;
+            if (best != ~0ull)
                 for (int j = tid; j < m; j += nt) {
                     const double v = __ldcg(f + j);
-                    if (v < 0.0) { const unsigned long long k = orderable(v); best = k < best ? k : best; }
+                    if (v < 0.0 && orderable(v) == best) { loc = j; break; }
                 }
-                best = block_min_u64(best, s);
-                int loc = SPX_NONE;
-                if (best != ~0ull)
-                    for (int j = tid; j < m; j += nt) {
-                        const double v = __ldcg(f + j);
-                        if (v < 0.0 && orderable(v) == best) { loc = j; break; }
-                    }
-                cl = block_min_int(loc, s);
-            }
+            cl = block_min_int(loc, s);
         }
         if (cl == SPX_NONE) {
             status = (r1 >= 0) ? SPX_INCORRECT : SPX_OPTIMAL;                                     // :88-89, :101-103
@@ -105,25 +120,22 @@ resident_loop_kernel(ResidentArgs a) {
         }
         // ---------------- K2: gather the column into shared memory, ratio test against the replica of b
         Ratio q = ratio_identity();
-        bool my_nan = false;
         for (int i = tid; i <= n; i += nt) {
             const double v = __ldcg(A + (int64_t)i * ld + cl);
             s_col[i] = v;
-            if (r1 < 0 && i < n) {
-                const bool first = (q.elig_row == SPX_NONE);
-                const bool is_nan = ratio_accumulate(q, i, v, s_b[i]);
-                if (first && q.elig_row != SPX_NONE) my_nan = is_nan;
-            }
+            if (r1 < 0 && i < n) ratio_accumulate(q, i, v, s_b[i]);
         }
         if (r1 >= 0) {
             r = r1;                                                                               // :91
             __syncthreads();
         } else {
-            // the NaN flag of the globally first eligible row: fold it into the reduction key
-            const int mine = (my_nan && q.elig_row != SPX_NONE) ? q.elig_row : SPX_NONE;
-            q = block_ratio_reduce(q, s);                                                         // syncs
-            const int nan_row = block_min_int(mine, s);
-            r = ratio_decide(q, nan_row == q.elig_row && q.elig_row != SPX_NONE);                 // :138-141
+            q = block_ratio_reduce(q, s);                                                         // syncs: s_col is complete
+            bool elig_nan = false;                        // a NaN ratio in the first eligible row is never replaced
+            if (q.elig_row != SPX_NONE) {
+                const double v = __ddiv_rn(s_b[q.elig_row], s_col[q.elig_row]);
+                elig_nan = (v != v);
+            }
+            r = ratio_decide(q, elig_nan);                                                        // :138-141
             if (r < 0) { status = SPX_NOCONV; break; }
         }
         p = s_col[r];
