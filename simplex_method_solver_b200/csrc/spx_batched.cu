@@ -117,7 +117,7 @@ __device__ __forceinline__ int warp_pick(const double *cur, int n, int m, int ru
 //               strictly sequential pivots): warp 0 prices the pivot, every warp updates its share
 //               of the cells, two block barriers per pivot.
 template <bool CTA>
-__global__ void __launch_bounds__(CTA ? 512 : 256, CTA ? 1 : 4)
+__global__ void __launch_bounds__(CTA ? 512 : 256, CTA ? 1 : 6)
 batched_kernel(BatchedArgs a, int warps_per_cta, int warp_doubles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_ctl[4];                               // CTA mode: {status, r, c} of warp 0's pick
