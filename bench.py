@@ -183,7 +183,7 @@ def config_dict(ngpu):
             if ngpu == 1 else "fused, column-sharded: cooperative pricing with the in-kernel NVLink exchange of keys and "
             "the pivot column, then one stream over the local columns per 8 pivots",
             "parallelism": "single GPU" if ngpu == 1 else
-            f"column-sharded x{ngpu}, one key + one pivot-column exchange per pivot over NVLink peer memory",
+            f"column-sharded x{ngpu}, one key + candidate-column exchange per pivot over NVLink peer memory",
             "l2_policy": "inputs (8.6 GB per pivot) far exceed the 126 MB L2; no flush needed",
             "rule": "reference (first-negative entering, max-negative-ratio leaving)"}
 
@@ -500,9 +500,23 @@ def run_ours(args):
     from simplex_method_solver_b200.parallel import FusedShardedTableau, PeerShardedTableau, ShardedTableau
     if args.exchange == "fused":
         # passes of 8 pivots: cooperative pricing with the in-kernel NVLink exchange, then ONE stream
-        # over the local columns applies them all (csrc/spx_fused.cu)
-        sh = FusedShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
-                                 depth=args.depth or fused_depth_for(world))
+        # over the local columns applies them all (csrc/spx_fused.cu).  If peer memory cannot be mapped on
+        # this box (no CUDA IPC / P2P between the GPUs) every rank falls back to the NCCL all-gather flow.
+        sh, err = None, ""
+        try:
+            sh = FusedShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
+                                     depth=args.depth or fused_depth_for(world))
+        except Exception as e:                       # noqa: BLE001 - reported below, then the documented fallback
+            err = f"{type(e).__name__}: {e}"
+        okf = torch.tensor([1 if sh is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if int(okf.item()) == 0:
+            log(f"[rank {rank}] peer-memory exchange unavailable ({err or 'a peer failed'}); falling back to --exchange nccl")
+            if sh is not None:
+                sh.close()
+            args.exchange = "nccl"
+            sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
+                                lookahead=not args.no_lookahead)
     elif args.exchange == "p2p":
         # C-side look-ahead loop, candidates exchanged by NVLink peer stores (csrc/spx_shard.cu)
         sh = PeerShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
@@ -576,7 +590,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(world), "clocks": clk.summary(),
+            "config": dict(config_dict(world), exchange=args.exchange), "clocks": clk.summary(),
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "update_kernel (K3), whole step incl. exchange",
                          "achieved": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9 / world,
