@@ -24,7 +24,22 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, n, m, seed, cap, mode, out):
+def _make_lp(n, m, seed, kind):
+    from simplex_method_solver_b200 import workloads as W
+    if kind == "dense":
+        return W.dense_lp(n, m, seed)
+    if kind == "late":                          # only the LAST columns price out at first: the entering column
+        rows, c = W.dense_lp(n, m, seed)        # lives on the last rank, later on several ranks
+        c[: int(0.95 * m)] = np.abs(c[: int(0.95 * m)])
+        return rows, c
+    rng = np.random.default_rng(seed)           # small integers: degenerate ties, phase-1 pivots, error endings
+    A = rng.integers(-3, 4, (n, m)).astype(float)
+    b = rng.integers(-2, 7, n).astype(float)
+    c = rng.integers(-3, 4, m).astype(float)
+    return np.hstack([A, b[:, None]]), c
+
+
+def _worker(rank, world, port, n, m, seed, cap, mode, kind, out):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -33,8 +48,7 @@ def _worker(rank, world, port, n, m, seed, cap, mode, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from simplex_method_solver_b200 import parallel as P
-        from simplex_method_solver_b200 import workloads as W
-        rows, c = W.dense_lp(n, m, seed)
+        rows, c = _make_lp(n, m, seed, kind)
         if mode == "fused":
             sh = P.FusedShardedTableau(n, m, rank, world, dev, trace_capacity=cap + 8, depth=5)
         elif mode == "p2p":
@@ -58,21 +72,23 @@ def _worker(rank, world, port, n, m, seed, cap, mode, out):
 
 
 @pytest.mark.parametrize("mode", ["fused", "p2p", "nccl", "nccl-ahead"])
-@pytest.mark.parametrize("n,m,cap", [(300, 2600, 150), (64, 1024, 400), (9, 40, 60)])   # last: ranks >= 1 own no columns
-def test_sharded_flow_on_real_gpus(mode, n, m, cap):
+@pytest.mark.parametrize("n,m,cap,kind", [(300, 2600, 150, "dense"), (64, 1024, 400, "dense"),
+                                          (9, 40, 60, "dense"),            # ranks >= 1 own no columns
+                                          (12, 1300, 60, "smallint"), (20, 1100, 80, "smallint"),
+                                          (24, 1100, 90, "late"), (40, 2100, 120, "late")])
+def test_sharded_flow_on_real_gpus(mode, n, m, cap, kind):
     import torch
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
     import oracle
-    from simplex_method_solver_b200 import workloads as W
-    rows, c = W.dense_lp(n, m, 7)
+    rows, c = _make_lp(n, m, 7, kind)
     o = oracle.solve(rows, c, max_pivots=cap)
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, m, 7, cap, mode, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, m, 7, cap, mode, kind, out)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(out.get(timeout=180) for _ in range(world))
