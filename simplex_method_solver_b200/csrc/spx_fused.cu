@@ -416,11 +416,11 @@ coop_price_kernel(CoopArgs ca) {
 //   key     then its 16-byte key + a release flag; every rank acquire-polls its local flags, takes the
 //           lexicographic minimum and reads the winner's plane.
 // The ratio test, the b column and the level bookkeeping are computed redundantly (bit-identically)
-// on every rank.  XBOX of one rank:  COLS[2][FUSE_MAX][R][cbd] | keys[FUSE_MAX+1][2][R][2] |
-// kflag[FUSE_MAX+1][2][R]  — one plane per (level, source rank): every rank that has a candidate stores
+// on every rank.  XBOX of one rank:  COLS[3][FUSE_MAX][R][cbd] | keys[2][FUSE_MAX+1][2][R][2] |
+// kflag[2][FUSE_MAX+1][2][R]  — one plane per (level, source rank): every rank that has a candidate stores
 // its candidate column SPECULATIVELY together with its key (one exchange per level instead of a key
-// round followed by a column round); COLS is double-buffered by pass parity because a fast rank may
-// price pass q+1 while a slow rank's update kernel still reads the planes of pass q.
+// round followed by a column round); the planes are triple-buffered by pass number (see the kernel),
+// keys and flags double-buffered by pass parity.
 constexpr int XB_MAX_RANKS = 16;
 
 struct XBoxLayout {
@@ -429,9 +429,9 @@ struct XBoxLayout {
 __host__ __device__ inline XBoxLayout xbox_layout(int64_t cbd, int R) {
     XBoxLayout L;
     L.cols_off = 0;
-    L.keys_off = (2LL * FUSE_MAX * R * cbd * 8 + 127) / 128 * 128;
-    L.kflag_off = L.keys_off + ((int64_t)(FUSE_MAX + 1) * 2 * R * 16 + 127) / 128 * 128;
-    L.bytes = L.kflag_off + ((int64_t)(FUSE_MAX + 1) * 2 * R * 8 + 127) / 128 * 128;
+    L.keys_off = (3LL * FUSE_MAX * R * cbd * 8 + 127) / 128 * 128;
+    L.kflag_off = L.keys_off + (2LL * (FUSE_MAX + 1) * 2 * R * 16 + 127) / 128 * 128;
+    L.bytes = L.kflag_off + (2LL * (FUSE_MAX + 1) * 2 * R * 8 + 127) / 128 * 128;
     return L;
 }
 
@@ -471,9 +471,10 @@ __device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigne
 // CTA 0 only: publish this rank's key of (level, kind) to every rank, collect everyone's, pick the
 // lexicographic minimum.  Returns through sel[0] = global column (or SPX_NONE), sel[1] = owner rank,
 // sel[2] = 0 / 1 (timeout).
-__device__ void exchange_keys(const ShardArgs &sa, const XBoxLayout &XL, int level, int kind,
+__device__ void exchange_keys(const ShardArgs &sa, const XBoxLayout &XL, int kpar, int level, int kind,
                               unsigned long long kh, unsigned long long kl, int *sel) {
     const int tid = threadIdx.x, R = sa.R;
+    level += kpar * (FUSE_MAX + 1);                     // the slot set of this pass parity
     __shared__ int s_to;
     if (tid == 0) s_to = 0;
     __syncthreads();
@@ -520,7 +521,13 @@ shard_price_kernel(ShardArgs sa) {
     const int G = gridDim.x, gtid = blockIdx.x * blockDim.x + tid, gn = G * blockDim.x;
     const int64_t ld = a.ld, cbd = a.cbd, col0 = sa.col0;
     const XBoxLayout XL = xbox_layout(cbd, sa.R);
-    const int par = (int)(sa.seq & 1ull);
+    // COL planes are TRIPLE-buffered by pass number: with look-ahead a fast rank can be pricing pass q+1
+    // (storing into every rank's planes) while a slow rank's update of pass q-1 still reads its planes —
+    // the slow rank's pricing of pass q, which the fast rank had to wait for, runs concurrently with that
+    // update.  Pass q+2 cannot start anywhere before every rank's update q-1 has finished.
+    const int par = (int)(sa.seq % 3ull);
+    const int par_prev = (int)((sa.seq + 2ull) % 3ull);
+    const int kpar = (int)(sa.seq & 1ull);               // key / flag slots: double-buffered by pass parity
     // this pass's COLS planes in MY box: plane (level l, source rank g) at COLS + (l * R + g) * cbd
     double *COLS = reinterpret_cast<double *>(sa.xbox[sa.rank] + XL.cols_off) + (int64_t)par * FUSE_MAX * sa.R * cbd;
     __shared__ const double *s_colp[2 * FUSE_MAX];       // per level: the winner's COL plane in MY box
@@ -544,7 +551,7 @@ shard_price_kernel(ShardArgs sa) {
         s_lvl[tid].d = pivot_div_prepare(sa.prev_plan->lvl[tid].p);
         s_rowp[tid] = sa.prev_ROWS + (int64_t)tid * ld;
         s_colp[tid] = reinterpret_cast<const double *>(sa.xbox[sa.rank] + XL.cols_off) +
-                      (((int64_t)(par ^ 1) * FUSE_MAX + tid) * sa.R + sa.prev_plan->owner[tid]) * cbd;
+                      (((int64_t)par_prev * FUSE_MAX + tid) * sa.R + sa.prev_plan->owner[tid]) * cbd;
     }
     __syncthreads();
 
@@ -661,7 +668,7 @@ shard_price_kernel(ShardArgs sa) {
         grid.sync();
         // ---------------- one exchange: key + flag (the column stores above are ordered before the flag)
         if (blockIdx.x == 0)
-            exchange_keys(sa, XL, i, kind, (cloc == SPX_NONE) ? ~0ull : kh,
+            exchange_keys(sa, XL, kpar, i, kind, (cloc == SPX_NONE) ? ~0ull : kh,
                           (cloc == SPX_NONE) ? ~0ull : (unsigned long long)(col0 + cloc), gsel);
         grid.sync();
         const int c = __ldcg(gsel + 0), owner = __ldcg(gsel + 1);
@@ -1028,6 +1035,7 @@ static cudaError_t launch_shard_price(const FusedCtx &c, const FusedWork &w, int
 }
 
 static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, int h, int minb, cudaStream_t stream) {
+    const int slot3 = (int)(c.seq % 3ull);               // the COL planes of this pass (c.seq = its pass number)
     static bool configured = false;
     cudaError_t e;
     if (!configured) {
@@ -1038,7 +1046,7 @@ static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, in
     const int64_t cbd = colbuf_doubles(c.n);
     const XBoxLayout XL = xbox_layout(cbd, c.R);
     const double *COLS = reinterpret_cast<const double *>(static_cast<unsigned char *>(c.xbox[c.rank]) + XL.cols_off) +
-                         (int64_t)h * FUSE_MAX * c.R * cbd;
+                         (int64_t)slot3 * FUSE_MAX * c.R * cbd;
     dim3 grid((unsigned)((c.m_loc + FUP_TC - 1) / FUP_TC), (unsigned)((c.n + 1 + FUP_TR - 1) / FUP_TR));
     if (grid.x == 0) return cudaSuccess;                     // a shard without columns only prices
     if (minb == 3)

@@ -45,7 +45,9 @@ def _worker(rank, world, port, n, m, seed, cap, mode, kind, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev,
+                            timeout=datetime.timedelta(seconds=120))
     try:
         from simplex_method_solver_b200 import parallel as P
         rows, c = _make_lp(n, m, seed, kind)
@@ -88,13 +90,19 @@ def test_sharded_flow_on_real_gpus(mode, n, m, cap, kind):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, m, 7, cap, mode, kind, out)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, m, 7, cap, mode, kind, out), daemon=True)
+             for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(out.get(timeout=180) for _ in range(world))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        got = dict(out.get(timeout=150) for _ in range(world))
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                      # a failed rank must not leave its peers spinning in a collective
+            if p.is_alive():
+                p.kill()
     body = np.zeros((n + 1, m))
     for r in range(world):
         g = got[r]
