@@ -64,6 +64,23 @@ def test_abi_constants_and_state_layout(native):
     assert L.spx_launch_count(1) >= 0 and L.spx_launch_count(0) == 0
 
 
+def test_host_side_layout_helpers_agree_with_python(native):
+    """Sizes the Python plumbing derives itself must match the library's (no device needed)."""
+    L = native.load()
+    for n in (9, 1000, 16384):
+        msgd = L.spx_shard_msg_doubles(n)
+        for world in (1, 2, 8):
+            # parallel.PeerMailboxes: gathered[2][world][msg] | flags[2][world]
+            flags_offset = (2 * world * msgd * 8 + 127) // 128 * 128
+            assert L.spx_mailbox_bytes(n, world) == flags_offset + (2 * world * 8 + 127) // 128 * 128
+            assert L.spx_fshard_xbox_bytes(n, world) > 3 * 8 * world * (n + 1) * 8      # 3 plane sets of 8 levels
+        assert L.spx_mailbox_bytes(n, 17) == -1 and L.spx_fshard_xbox_bytes(n, 17) == -1
+        for m in (2, 2000, 32768):
+            assert L.spx_fused_workspace_bytes(n, m) >= 2 * 8 * L.spx_ld(m) * 8 + 8 * L.spx_colbuf_doubles(n) * 8
+            assert L.spx_solve_workspace_bytes(n) >= 128 + (n + 1) * 8 + msgd * 8
+    assert native.LOOP_MODES[None] == 0 and native.LOOP_MODES["fused"] == 4 and native.LOOP_MODES[True] == 2
+
+
 def test_argument_validation_reports_text(native):
     """Entry points reject bad arguments before touching the device (no GPU needed)."""
     L = native.load()
