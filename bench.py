@@ -175,13 +175,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def config_dict(ngpu):
+def config_dict(ngpu, exchange="fused"):
     return {"workload": "cfg4: dense LP D(n=16384, m=32768, seed=0), fp64 tableau 4.295 GB (x2 ping-pong)",
             "n": N_ROWS, "m": M_COLS, "cells": cells(N_ROWS, M_COLS),
             "pivots_per_step": PIVOTS_PER_STEP,
             "loop": "fused: 8 pivots priced from the stored table, then ONE stream over the body applies them (csrc/spx_fused.cu)"
             if ngpu == 1 else "fused, column-sharded: cooperative pricing with the in-kernel NVLink exchange of keys and "
-            "the pivot column, then one stream over the local columns per 8 pivots",
+            "the pivot column, then one stream over the local columns per 8 pivots" if exchange == "fused" else
+            "pivot at a time, column-sharded: look-ahead pricing of pivot k+1 during update k (csrc/spx_shard.cu, spx_pick.cu)",
             "parallelism": "single GPU" if ngpu == 1 else
             f"column-sharded x{ngpu}, one key + candidate-column exchange per pivot over NVLink peer memory",
             "l2_policy": "inputs (8.6 GB per pivot) far exceed the 126 MB L2; no flush needed",
@@ -498,6 +499,7 @@ def run_ours(args):
 
     # ---------------- N > 1: column-sharded, one process per GPU ---------------------------
     from simplex_method_solver_b200.parallel import FusedShardedTableau, PeerShardedTableau, ShardedTableau
+    fallback_note = None
     if args.exchange == "fused":
         # passes of 8 pivots: cooperative pricing with the in-kernel NVLink exchange, then ONE stream
         # over the local columns applies them all (csrc/spx_fused.cu).  If peer memory cannot be mapped on
@@ -512,11 +514,36 @@ def run_ours(args):
         dist.all_reduce(okf, op=dist.ReduceOp.MIN)
         if int(okf.item()) == 0:
             log(f"[rank {rank}] peer-memory exchange unavailable ({err or 'a peer failed'}); falling back to --exchange nccl")
+            fallback_note = f"peer memory unavailable ({err or 'on a peer'})"
             if sh is not None:
                 sh.close()
             args.exchange = "nccl"
             sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
                                 lookahead=not args.no_lookahead)
+        else:
+            # preflight: a few passes against the golden prefix on EVERY rank before anything is timed; a rank
+            # that times out on a peer (SPX_PEER_TIMEOUT) or diverges sends all ranks to the pivot-at-a-time
+            # peer-mailbox loop instead (csrc/spx_shard.cu), and the printed config says so
+            pre, why = 96, ""
+            try:
+                sh.load(rows, c, max_pivots=pre + 64)
+                sh.run(pre)
+                stp = sh.sync()
+                trp = sh.trace[:pre].cpu().numpy()
+                if stp.status != N.PIVOT or stp.npiv != pre:
+                    why = f"status {stp.status} after {stp.npiv} pivots"
+                elif not (trp == gold[:pre]).all():
+                    why = "pivot sequence differs from the golden prefix"
+            except Exception as e:                   # noqa: BLE001
+                why = f"{type(e).__name__}: {e}"
+            okf = torch.tensor([0 if why else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if int(okf.item()) == 0:
+                log(f"[rank {rank}] fused exchange failed its preflight ({why or 'on a peer'}); falling back to --exchange p2p")
+                fallback_note = f"fused preflight failed ({why or 'on a peer'})"
+                sh.close()
+                args.exchange = "p2p"
+                sh = PeerShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
     elif args.exchange == "p2p":
         # C-side look-ahead loop, candidates exchanged by NVLink peer stores (csrc/spx_shard.cu)
         sh = PeerShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
@@ -554,7 +581,7 @@ def run_ours(args):
     # ---------------- e2e at N GPUs: every rank uploads ITS column block from pinned host memory, the
     # ranks pivot together, every rank reads its state and trace back; wall clock between barriers, max over ranks
     e2e = None
-    if args.exchange == "fused":
+    if args.exchange in ("fused", "p2p"):
         blk = torch.empty((N_ROWS, sh.m_loc + 1), dtype=torch.float64).pin_memory()
         blk.numpy()[:, : sh.m_loc] = rows[:, sh.col0: sh.col0 + sh.m_loc]
         blk.numpy()[:, sh.m_loc] = rows[:, M_COLS]
@@ -581,7 +608,7 @@ def run_ours(args):
                "h2d_bytes_per_step": int(8 * (N_ROWS * (M_COLS + world) + M_COLS)),
                "d2h_bytes_per_step": int(world * (tr2.nbytes + 128)), "steps": e2e_steps,
                "ms_per_step": 1e3 * float(tmax.item()),
-               "api": f"FusedShardedTableau.load_local(pinned_block, c_block); run({P}); sync() on every rank"}
+               "api": f"{type(sh).__name__}.load_local(pinned_block, c_block); run({P}); sync() on every rank"}
         del blk
     del rows
     if args.exchange in ("p2p", "fused"):    batched = batched_leg(dev, rank, world, dist) if not args.no_batched else None
@@ -590,7 +617,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(config_dict(world), exchange=args.exchange), "clocks": clk.summary(),
+            "config": dict(config_dict(world, args.exchange), exchange=args.exchange,
+                           **({"exchange_fallback": fallback_note} if fallback_note else {})),
+            "clocks": clk.summary(),
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "update_kernel (K3), whole step incl. exchange",
                          "achieved": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9 / world,

@@ -554,6 +554,11 @@ class PeerShardedTableau(ShardedTableau):
         N.call("spx_shard_reset", self.handle)
         self._cur = 0
 
+    def load_local(self, block, function_block, max_pivots: int):
+        super().load_local(block, function_block, max_pivots)
+        N.call("spx_shard_reset", self.handle)
+        self._cur = 0
+
     def step(self):
         self.run(1)
 
