@@ -444,15 +444,18 @@ def test_column_sharded_ranks_emulated_on_one_gpu(spx, world, n, m, kind, lookah
     """The sharded CUDA kernels (candidate / select / update with col0 > 0, and their look-ahead
     forms) with `world` ranks emulated in one process: the phases of every rank run in lockstep and
     the all-gather is a device copy.  Trace, labels, b and every body cell equal the oracle's."""
-    from simplex_method_solver_b200 import parallel as P
-    torch = spx.torch
     if kind == "dense":
         rows, c = W.dense_lp(n, m, 3)
     else:
         rng = np.random.default_rng(5)
         rows = np.hstack([rng.integers(-3, 4, (n, m)).astype(float), rng.integers(-2, 7, (n, 1)).astype(float)])
         c = rng.integers(-3, 4, m).astype(float)
-    cap = 40
+    _emulated_ranks(spx, world, n, m, rows, c, 40, lookahead, exchange)
+
+
+def _emulated_ranks(spx, world, n, m, rows, c, cap, lookahead, exchange):
+    from simplex_method_solver_b200 import parallel as P
+    torch = spx.torch
     o = oracle.solve(rows, c, max_pivots=cap)
     boxes = None
     if exchange == "mailbox":                          # NVLink-style peer stores + flags, all boxes in one process
@@ -674,3 +677,21 @@ def test_cfg4_16k_x_32k_prefix(spx, cfg_digests):
         assert [float(v).hex() for v in f[:4]] == g["marks"][str(mark)]["f_first4"]
         assert hashlib.sha256(b.tobytes()).hexdigest() == g["marks"][str(mark)]["b_sha256"]
         assert hashlib.sha256(f.tobytes()).hexdigest() == g["marks"][str(mark)]["f_sha256"]
+
+
+# --------------------------------------------------------------------------- owner rank != 0 (kept last in this file)
+@pytest.mark.parametrize("exchange", ["copy", "mailbox"])
+@pytest.mark.parametrize("lookahead", [False, True])
+@pytest.mark.parametrize("world,n,m,cap", [(2, 24, 1100, 60), (3, 64, 1600, 100), (4, 64, 1600, 100), (4, 40, 2100, 120)])
+def test_column_sharded_ranks_emulated_entering_column_on_late_ranks(spx, world, n, m, cap, lookahead, exchange):
+    """Same emulation as test_column_sharded_ranks_emulated_on_one_gpu on LPs whose entering column is owned by
+    the LATER ranks and keeps changing owner (util.make_lp 'late'): in the dense and small-integer cases, and
+    in the cfg4 prefix bench.py runs, rank 0 owns every entering column, so the winner != 0 branch of the
+    select kernels and the pivot column outside rank 0's block are only exercised here."""
+    from util import make_lp, owners_of
+    from simplex_method_solver_b200.parallel import column_block
+    rows, c = make_lp(n, m, 7, "late")
+    o = oracle.solve(rows, c, max_pivots=cap)
+    own = owners_of(o.trace.tolist(), [column_block(m, r, world) for r in range(world)])
+    assert sum(g != 0 for g in own) >= 30                                 # the case really is what it claims
+    _emulated_ranks(spx, world, n, m, rows, c, cap, lookahead, exchange)

@@ -25,18 +25,8 @@ def _free_port():
 
 
 def _make_lp(n, m, seed, kind):
-    from simplex_method_solver_b200 import workloads as W
-    if kind == "dense":
-        return W.dense_lp(n, m, seed)
-    if kind == "late":                          # only the LAST columns price out at first: the entering column
-        rows, c = W.dense_lp(n, m, seed)        # lives on the last rank, later on several ranks
-        c[: int(0.95 * m)] = np.abs(c[: int(0.95 * m)])
-        return rows, c
-    rng = np.random.default_rng(seed)           # small integers: degenerate ties, phase-1 pivots, error endings
-    A = rng.integers(-3, 4, (n, m)).astype(float)
-    b = rng.integers(-2, 7, n).astype(float)
-    c = rng.integers(-3, 4, m).astype(float)
-    return np.hstack([A, b[:, None]]), c
+    from util import make_lp
+    return make_lp(n, m, seed, kind)
 
 
 def _worker(rank, world, port, n, m, seed, cap, mode, kind, out):
@@ -85,7 +75,8 @@ EXTENDED = os.environ.get("SPX_MULTIGPU_EXTENDED", "0") == "1"
 @pytest.mark.parametrize("n,m,cap,kind", [(300, 2600, 150, "dense"), (64, 1024, 400, "dense"),
                                           (9, 40, 60, "dense"),            # ranks >= 1 own no columns
                                           (12, 1300, 60, "smallint"), (20, 1100, 80, "smallint"),
-                                          (24, 1100, 90, "late"), (40, 2100, 120, "late")])
+                                          (24, 1100, 90, "late"), (40, 2100, 120, "late"),
+                                          (64, 1600, 100, "late")])         # owners 19/3/41/37 at world 4
 def test_sharded_flow_on_real_gpus(mode, n, m, cap, kind):
     import torch
     if kind != "dense" and not EXTENDED:

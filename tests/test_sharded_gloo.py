@@ -72,14 +72,8 @@ def _sharded_worker(rank, world, port, n, m, seed, cap, kind, lookahead, out):
 
 
 def _make_lp(n, m, seed, kind):
-    from simplex_method_solver_b200 import workloads as W
-    if kind == "dense":
-        return W.dense_lp(n, m, seed)
-    rng = np.random.default_rng(seed)
-    A = rng.integers(-3, 4, (n, m)).astype(float)
-    b = rng.integers(-2, 7, n).astype(float)
-    c = rng.integers(-3, 4, m).astype(float)
-    return np.hstack([A, b[:, None]]), c
+    from util import make_lp
+    return make_lp(n, m, seed, kind)
 
 
 def _run_world(world, n, m, seed, cap, kind, lookahead):
@@ -102,6 +96,7 @@ def _run_world(world, n, m, seed, cap, kind, lookahead):
     (2, 24, 1100, "dense", 3),       # 3 column tiles over 2 ranks: uneven blocks
     (3, 12, 1300, "smallint", 5),    # degenerate ties, phase-1 pivots, error endings
     (2, 9, 40, "smallint", 8),       # fewer tiles than ranks: rank 1 owns no columns
+    (3, 64, 1600, "late", 7),        # entering columns on ranks 1 and 2, ~30 owner changes in 60 pivots
 ])
 def test_sharded_trace_equals_single_process_oracle(world, n, m, kind, seed, lookahead):
     import oracle
