@@ -854,6 +854,146 @@ update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cb
     }
 }
 
+// ---- EXPERIMENTAL variant of the fused update (selected with SPX_OPT_FUSE_VARIANT != 0; not the default,
+// written after round 1's GPU budget was spent — see DESIGN.md "What comes next", item 2).  Same arithmetic
+// and the same bits as update_fused_kernel; what changes is the schedule:
+//   * tile height `tr` is a runtime value (SPX_OPT_FUSE_TILE_ROWS: 32..256): the 8 ROW slices of a column
+//     tile and the staging barrier are paid once per tr rows instead of once per 32;
+//   * PREFETCH: the next 8-row batch is loaded into a second register set before the current one is
+//     computed, so a warp always has 8 x 512 B of its own reads in flight;
+//   * the slow path (apply_level with its row / column tests) is taken per 8-row batch and per WARP — a
+//     batch that holds a pivot row, or a warp whose 64 columns hold a pivot column — instead of per tile.
+template <int MINB, bool PREFETCH>
+__global__ void __launch_bounds__(FUP_THREADS, MINB)
+update_fused2_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R, int tr,
+                     const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
+                     const double *__restrict__ COLS) {
+    const int f = plan->f;
+    if (f <= 0) return;
+    extern __shared__ __align__(128) unsigned char fus2_raw[];
+    double (*s_rows)[FUP_TC] = reinterpret_cast<double (*)[FUP_TC]>(fus2_raw);          // [FUSE_MAX][FUP_TC]
+    double *s_cols = reinterpret_cast<double *>(fus2_raw + sizeof(double) * FUSE_MAX * FUP_TC);   // [FUSE_MAX][tr]
+    __shared__ LevelDiv s_lvl[FUSE_MAX];
+    __shared__ alignas(8) uint64_t s_bar;
+
+    const int src = plan->src;
+    const double *__restrict__ Ain = src ? A1 : A0;
+    double *__restrict__ Aout = src ? A0 : A1;
+
+    const int tid = threadIdx.x;
+    const int j0 = blockIdx.x * FUP_TC;
+    const int i0 = blockIdx.y * tr;
+    const int rows = min(tr, n + 1 - i0);
+    const uint32_t row_bytes = (uint32_t)(min((int64_t)FUP_TC, ld - j0) * 8);
+    const uint32_t col_bytes = (uint32_t)(min((int64_t)tr, cbd - i0) * 8);            // planes hold cbd >= n + 1 cells
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&s_bar, (uint32_t)f * (row_bytes + col_bytes));
+        for (int l = 0; l < f; ++l) {
+            bulk_g2s(s_rows[l], ROWS + (int64_t)l * ld + j0, row_bytes, &s_bar);
+            bulk_g2s(s_cols + (int64_t)l * tr, COLS + ((int64_t)l * R + plan->owner[l]) * cbd + i0, col_bytes, &s_bar);
+        }
+    }
+    if (tid < f) {
+        s_lvl[tid].r = plan->lvl[tid].r;
+        const int64_t cl = (int64_t)plan->lvl[tid].c - col0;
+        s_lvl[tid].c = (cl >= 0 && cl < m) ? (int)cl : -1;
+        s_lvl[tid].d = pivot_div_prepare(plan->lvl[tid].p);
+    }
+    __syncthreads();
+
+    const int j = j0 + 2 * tid;
+    const bool active = j < m;
+    const double *srcp = Ain + (int64_t)i0 * ld + j;
+    double *dstp = Aout + (int64_t)i0 * ld + j;
+    double2 t[FUP_UNROLL], tn[FUP_UNROLL];
+    // the first batch does not depend on the staged slices: issue it before waiting for them
+#pragma unroll
+    for (int u = 0; u < FUP_UNROLL; ++u)
+        t[u] = (active && u < rows) ? ld_stream(srcp + (int64_t)u * ld) : make_double2(1.0, 1.0);
+    mbar_wait(&s_bar, 0);
+    if (!active) return;
+
+    // warp-uniform: does a pivot column of any level fall into this warp's 64 columns?
+    const int wj0 = j0 + 64 * (tid >> 5);
+    bool colspecial = false;
+    for (int l = 0; l < f; ++l) {
+        const int cl = s_lvl[l].c;
+        colspecial = colspecial || (cl >= wj0 && cl < wj0 + 64);
+    }
+
+    for (int ii = 0; ii < rows; ii += FUP_UNROLL) {
+        if (PREFETCH) {
+#pragma unroll
+            for (int u = 0; u < FUP_UNROLL; ++u)
+                tn[u] = (ii + FUP_UNROLL + u < rows) ? ld_stream(srcp + (int64_t)(ii + FUP_UNROLL + u) * ld)
+                                                     : make_double2(1.0, 1.0);
+        }
+        bool special = colspecial;
+        for (int l = 0; l < f; ++l) {
+            const int rl = s_lvl[l].r;
+            special = special || (rl >= i0 + ii && rl < i0 + ii + FUP_UNROLL);
+        }
+        if (!special) {
+            bool ok = true;
+            for (int l = 0; l < f; ++l) {
+                const double2 rj = *reinterpret_cast<const double2 *>(&s_rows[l][2 * tid]);
+                const PivotDiv d = s_lvl[l].d;
+                const double *cl = s_cols + (int64_t)l * tr + ii;
+#pragma unroll
+                for (int u = 0; u < FUP_UNROLL; ++u) {
+                    const double ci = cl[u];
+                    t[u].x = cell_update_unchecked(t[u].x, d, rj.x, ci, ok);
+                    t[u].y = cell_update_unchecked(t[u].y, d, rj.y, ci, ok);
+                }
+            }
+            if (__builtin_expect(!ok, 0)) {
+                // a quotient left the fast path's exponent range: redo the batch from the stored cells
+#pragma unroll
+                for (int u = 0; u < FUP_UNROLL; ++u)
+                    t[u] = (ii + u < rows) ? ld_stream(srcp + (int64_t)(ii + u) * ld) : make_double2(1.0, 1.0);
+                for (int l = 0; l < f; ++l) {
+                    const double2 rj = *reinterpret_cast<const double2 *>(&s_rows[l][2 * tid]);
+                    const PivotDiv d = s_lvl[l].d;
+                    const double *cl = s_cols + (int64_t)l * tr + ii;
+#pragma unroll
+                    for (int u = 0; u < FUP_UNROLL; ++u) {
+                        const double ci = cl[u];
+                        t[u].x = cell_update(t[u].x, d, rj.x, ci);
+                        t[u].y = cell_update(t[u].y, d, rj.y, ci);
+                    }
+                }
+            }
+        } else {
+            for (int l = 0; l < f; ++l) {
+                const double2 rj = *reinterpret_cast<const double2 *>(&s_rows[l][2 * tid]);
+                const LevelDiv L = s_lvl[l];
+                const double *cl = s_cols + (int64_t)l * tr + ii;
+#pragma unroll
+                for (int u = 0; u < FUP_UNROLL; ++u) {
+                    const int ti = i0 + ii + u;
+                    const double ci = cl[u];
+                    t[u].x = apply_level(t[u].x, ti, j, L, rj.x, ci);
+                    t[u].y = apply_level(t[u].y, ti, j + 1, L, rj.y, ci);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FUP_UNROLL; ++u)
+            if (ii + u < rows) st_stream(dstp + (int64_t)(ii + u) * ld, t[u]);
+        if (PREFETCH) {
+#pragma unroll
+            for (int u = 0; u < FUP_UNROLL; ++u) t[u] = tn[u];
+        } else if (ii + FUP_UNROLL < rows) {
+#pragma unroll
+            for (int u = 0; u < FUP_UNROLL; ++u)
+                t[u] = (ii + FUP_UNROLL + u < rows) ? ld_stream(srcp + (int64_t)(ii + FUP_UNROLL + u) * ld)
+                                                     : make_double2(1.0, 1.0);
+        }
+    }
+}
+
 } // namespace
 
 namespace spx_launch {
@@ -900,6 +1040,43 @@ FusedWork carve_work(void *work, int n, int64_t ld) {
 }
 
 int64_t fused_workspace_bytes(int n, int64_t ld) { return carve_work(nullptr, n, ld).bytes; }
+
+int64_t get_option(int key);
+
+// SPX_OPT_FUSE_VARIANT != 0: the experimental update kernel (bit 0: register prefetch of the next batch);
+// SPX_OPT_FUSE_TILE_ROWS: its tile height (0 = 64).  Returns cudaErrorNotSupported when the default kernel is selected.
+static cudaError_t launch_update_variant(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R,
+                                         const PlanHeader *plan, const double *ROWS, const double *COLS, int minb,
+                                         cudaStream_t stream) {
+    const int variant = (int)get_option(SPX_OPT_FUSE_VARIANT);
+    if (variant == 0) return cudaErrorNotSupported;
+    int tr = (int)get_option(SPX_OPT_FUSE_TILE_ROWS);
+    if (tr <= 0) tr = 64;
+    const bool prefetch = (variant & 1) != 0;
+    const size_t smem = sizeof(double) * FUSE_MAX * (FUP_TC + (size_t)tr);
+    static bool configured = false;
+    cudaError_t e;
+    if (!configured) {
+        const int cap = (int)(sizeof(double) * FUSE_MAX * (FUP_TC + 256));
+#define SPX_CFG2(MB, PF) \
+        if ((e = cudaFuncSetAttribute(update_fused2_kernel<MB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
+        SPX_CFG2(2, false) SPX_CFG2(3, false) SPX_CFG2(4, false) SPX_CFG2(2, true) SPX_CFG2(3, true) SPX_CFG2(4, true)
+#undef SPX_CFG2
+        configured = true;
+    }
+    dim3 grid((unsigned)((m + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + tr - 1) / tr));
+    if (grid.x == 0) return cudaSuccess;
+#define SPX_RUN2(MB, PF) \
+    update_fused2_kernel<MB, PF><<<grid, FUP_THREADS, smem, stream>>>(A0, A1, n, m, ld, cbd, col0, R, tr, plan, ROWS, COLS)
+    if (prefetch) {
+        if (minb == 2) SPX_RUN2(2, true); else if (minb == 3) SPX_RUN2(3, true); else SPX_RUN2(4, true);
+    } else {
+        if (minb == 2) SPX_RUN2(2, false); else if (minb == 3) SPX_RUN2(3, false); else SPX_RUN2(4, false);
+    }
+#undef SPX_RUN2
+    spx_host::count_launch();
+    return cudaGetLastError();
+}
 
 static int g_coop_ctas = -1;      // co-resident CTAs of coop_price_kernel (0: cooperative launch unavailable)
 
@@ -950,6 +1127,8 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
     if (e != cudaSuccess) return e;
     if (phase != 2) spx_host::count_launch();
     if (phase == 1) return cudaSuccess;
+    if ((e = launch_update_variant(A0, A1, n, m, ld, cbd, col0, 1, plan, ROWS, COLS, minb, stream)) != cudaErrorNotSupported)
+        return e;
     static bool configured = false;
     if (!configured) {
         if ((e = cudaFuncSetAttribute(update_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
@@ -1047,6 +1226,9 @@ static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, in
     const XBoxLayout XL = xbox_layout(cbd, c.R);
     const double *COLS = reinterpret_cast<const double *>(static_cast<unsigned char *>(c.xbox[c.rank]) + XL.cols_off) +
                          (int64_t)slot3 * FUSE_MAX * c.R * cbd;
+    if ((e = launch_update_variant(c.A[0], c.A[1], c.n, c.m_loc, c.ld, cbd, c.col0, c.R, w.plan[h], w.ROWS[h], COLS, minb,
+                                   stream)) != cudaErrorNotSupported)
+        return e;
     dim3 grid((unsigned)((c.m_loc + FUP_TC - 1) / FUP_TC), (unsigned)((c.n + 1 + FUP_TR - 1) / FUP_TR));
     if (grid.x == 0) return cudaSuccess;                     // a shard without columns only prices
     if (minb == 3)

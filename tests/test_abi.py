@@ -81,6 +81,20 @@ def test_host_side_layout_helpers_agree_with_python(native):
     assert native.LOOP_MODES[None] == 0 and native.LOOP_MODES["fused"] == 4 and native.LOOP_MODES[True] == 2
 
 
+def test_options_validate_their_ranges(native):
+    L = native.load()
+    try:
+        assert L.spx_get_option(10) == 0 and L.spx_get_option(11) == 0 and L.spx_get_option(7) == 0   # defaults
+        assert L.spx_set_option(10, 3) == 0 and L.spx_get_option(10) == 3
+        assert L.spx_set_option(10, 4) != 0 and L.spx_set_option(10, -1) != 0
+        assert L.spx_set_option(11, 40) == 0 and L.spx_get_option(11) == 40
+        assert L.spx_set_option(11, 12) != 0 and L.spx_set_option(11, 264) != 0
+        assert L.spx_set_option(6, 9) != 0 and L.spx_set_option(99, 0) != 0
+    finally:
+        L.spx_set_option(10, 0)
+        L.spx_set_option(11, 0)
+
+
 def test_argument_validation_reports_text(native):
     """Entry points reject bad arguments before touching the device (no GPU needed)."""
     L = native.load()

@@ -29,6 +29,12 @@ class loop_mode:
         if self.name == "fused-gpuwide":               # ... with the whole-GPU cooperative pricing kernel forced on
             assert N.lib().spx_set_option(8, 2) == 0
             return "fused"
+        if isinstance(self.name, str) and self.name.startswith("fused-x"):   # "fused-x<variant>-<tile rows>[-<minb>]":
+            parts = self.name[len("fused-x"):].split("-")                    # the experimental update kernel
+            assert N.lib().spx_set_option(10, int(parts[0])) == 0
+            assert N.lib().spx_set_option(11, int(parts[1])) == 0
+            assert N.lib().spx_set_option(7, int(parts[2]) if len(parts) > 2 else 0) == 0
+            return "fused"
         return self.name
 
     def __exit__(self, *a):
@@ -37,6 +43,9 @@ class loop_mode:
             N.lib().spx_set_option(9, 0)
         if self.name == "fused-gpuwide":
             N.lib().spx_set_option(8, 0)
+        if isinstance(self.name, str) and self.name.startswith("fused-x"):
+            for k in (10, 11, 7):
+                N.lib().spx_set_option(k, 0)
 
 
 @pytest.fixture(scope="module")
@@ -695,3 +704,34 @@ def test_column_sharded_ranks_emulated_entering_column_on_late_ranks(spx, world,
     own = owners_of(o.trace.tolist(), [column_block(m, r, world) for r in range(world)])
     assert sum(g != 0 for g in own) >= 30                                 # the case really is what it claims
     _emulated_ranks(spx, world, n, m, rows, c, cap, lookahead, exchange)
+
+
+# --------------------------------------------------------------------------- experimental fused update kernel
+EXPERIMENTAL = __import__("os").environ.get("SPX_EXPERIMENTAL", "0") == "1"
+X_MODES = ["fused-x2-32", "fused-x2-64", "fused-x2-256", "fused-x3-64-2", "fused-x3-128-2", "fused-x3-40-3", "fused-x3-8"]
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="update_fused2_kernel (SPX_OPT_FUSE_VARIANT) was written after round 1's GPU "
+                    "budget was spent and has not run on hardware: set SPX_EXPERIMENTAL=1")
+@pytest.mark.parametrize("mode", X_MODES)
+def test_experimental_fused_update_variant(spx, ref_cases, cfg_digests, mode):
+    """Every schedule of the experimental fused update kernel (tile height, register prefetch, occupancy target)
+    must produce the default kernel's bits: ragged shapes in steps of 1..9 pivots, the reference's golden cases,
+    and the first 300 pivots of cfg2."""
+    with loop_mode(mode) as mode_:
+        for n, m in [(1, 2), (3, 1), (7, 15), (65, 513), (130, 1030), (257, 100), (300, 700), (40, 2049)]:
+            _ragged_loop(spx, n, m, mode_)
+        for case in ref_cases:
+            rows, c = case_inputs(case)
+            sm = spx.simplex.SimplexMethod(rows, c, engine="stream")
+            sol = sm.solve(max_pivots=case["cap"], chunk=5, lookahead=mode_)
+            assert sol.status == END_TO_STATUS[case["end"]], case["name"]
+            assert sol.trace.tolist() == case["trace"], case["name"]
+            assert table_sha(sm._dev.export_flat(sm._npiv)) == case["final_table_sha256"], case["name"]
+        rows, c = W.dense_lp(1000, 2000, 0)
+        o = oracle.solve(rows, c, max_pivots=300)
+        dev = spx.engine.DeviceTableau(1000, 2000, trace_capacity=400)
+        dev.load(rows, c, max_pivots=300)
+        dev.solve(stop_after=300, lookahead=mode_)
+        assert dev.trace[:300].cpu().numpy().tolist() == o.trace.tolist()
+        assert np.array_equal(bits(dev.export_flat(300)), bits(o.table))
