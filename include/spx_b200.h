@@ -101,7 +101,7 @@ int64_t     spx_launch_count(int reset);
 #define SPX_OPT_FUSE_MIN_BLOCKS  7  /* fused update kernel: resident CTAs per SM its register budget targets (2..4, 0 = default 4) */
 #define SPX_OPT_FUSE_PRICING     8  /* fused loop pricing kernel: 0 auto, 1 one CTA, 2 whole-GPU cooperative */
 #define SPX_OPT_FUSE_LOOKAHEAD   9  /* fused loop in spx_solve: 1 = price pass q+1 on a side stream during update q (default 0: off on one GPU) */
-#define SPX_OPT_FUSE_VARIANT     10 /* fused update kernel: 0 default; EXPERIMENTAL: 2 = runtime tile height + per-warp slow path, 3 = 2 + register prefetch of the next batch */
+#define SPX_OPT_FUSE_VARIANT     10 /* fused update kernel: 0 default; EXPERIMENTAL (bits): 2 = runtime tile height + per-warp slow path, +1 = register prefetch of the next batch, +4 = two-instruction range guard */
 #define SPX_OPT_FUSE_TILE_ROWS   11 /* experimental fused update kernel: rows per tile (0 = 64; a multiple of 8 <= 256) */
 int         spx_set_option(int32_t option, int64_t value);
 int64_t     spx_get_option(int32_t option);

@@ -862,8 +862,31 @@ update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cb
 //   * PREFETCH: the next 8-row batch is loaded into a second register set before the current one is
 //     computed, so a warp always has 8 x 512 B of its own reads in flight;
 //   * the slow path (apply_level with its row / column tests) is taken per 8-row batch and per WARP — a
-//     batch that holds a pivot row, or a warp whose 64 columns hold a pivot column — instead of per tile.
-template <int MINB, bool PREFETCH>
+//     batch that holds a pivot row, or a warp whose 64 columns hold a pivot column — instead of per tile;
+//   * GUARD2: the accumulated range test of pivot_div_unchecked, qlo <= (hi & 0x7fffffff) <= 0x7f800000, as
+//     ONE subtraction and ONE unsigned compare per quotient: doubling hi drops the sign bit, so the test is
+//     (2 * hi - 2 * qlo) mod 2^32 < 0xff000001 - 2 * qlo  (and "< 0", never true, when qlo is the
+//     always-fail sentinel 0x7f800001).
+__device__ __forceinline__ double cell_update_guard2(double t, const PivotDiv &d, double rj, double ci,
+                                                     unsigned q2, unsigned qr, bool &ok) {
+    const double a   = __dsub_rn(__dmul_rn(t, d.p), __dmul_rn(rj, ci));
+    const double q0  = __dmul_rn(a, d.y);
+    const double rem = __fma_rn(-d.p, q0, a);
+    const double q1  = __fma_rn(d.y, rem, q0);
+    unsigned tdiff;                                                 // 2 * hi - 2 * qlo in ONE instruction (IMAD)
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(tdiff) : "r"((unsigned)__double2hiint(q1)), "r"(0u - q2));
+    ok = ok && (tdiff < qr);
+    return q1;
+}
+
+__device__ __forceinline__ void load_cols8(double (&cv)[FUP_UNROLL], const double *p) {
+    static_assert(FUP_UNROLL == 8, "four 128-bit shared loads");
+    const double2 *p2 = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const double2 v = p2[u]; cv[2 * u] = v.x; cv[2 * u + 1] = v.y; }
+}
+
+template <int MINB, bool PREFETCH, bool GUARD2>
 __global__ void __launch_bounds__(FUP_THREADS, MINB)
 update_fused2_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R, int tr,
                      const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
@@ -940,12 +963,20 @@ update_fused2_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t c
             for (int l = 0; l < f; ++l) {
                 const double2 rj = *reinterpret_cast<const double2 *>(&s_rows[l][2 * tid]);
                 const PivotDiv d = s_lvl[l].d;
-                const double *cl = s_cols + (int64_t)l * tr + ii;
+                double cv[FUP_UNROLL];                               // tr and ii are multiples of 8: 64-byte aligned
+                load_cols8(cv, s_cols + (int64_t)l * tr + ii);
+                const unsigned q2 = d.qlo + d.qlo;                                   // qlo <= 0x7f800001: no overflow
+                const unsigned qr = (d.qlo > 0x7f800000u) ? 0u : 0xff000001u - q2;
 #pragma unroll
                 for (int u = 0; u < FUP_UNROLL; ++u) {
-                    const double ci = cl[u];
-                    t[u].x = cell_update_unchecked(t[u].x, d, rj.x, ci, ok);
-                    t[u].y = cell_update_unchecked(t[u].y, d, rj.y, ci, ok);
+                    const double ci = cv[u];
+                    if (GUARD2) {
+                        t[u].x = cell_update_guard2(t[u].x, d, rj.x, ci, q2, qr, ok);
+                        t[u].y = cell_update_guard2(t[u].y, d, rj.y, ci, q2, qr, ok);
+                    } else {
+                        t[u].x = cell_update_unchecked(t[u].x, d, rj.x, ci, ok);
+                        t[u].y = cell_update_unchecked(t[u].y, d, rj.y, ci, ok);
+                    }
                 }
             }
             if (__builtin_expect(!ok, 0)) {
@@ -956,10 +987,11 @@ update_fused2_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t c
                 for (int l = 0; l < f; ++l) {
                     const double2 rj = *reinterpret_cast<const double2 *>(&s_rows[l][2 * tid]);
                     const PivotDiv d = s_lvl[l].d;
-                    const double *cl = s_cols + (int64_t)l * tr + ii;
+                    double cv[FUP_UNROLL];                               // tr and ii are multiples of 8: 64-byte aligned
+                load_cols8(cv, s_cols + (int64_t)l * tr + ii);
 #pragma unroll
                     for (int u = 0; u < FUP_UNROLL; ++u) {
-                        const double ci = cl[u];
+                        const double ci = cv[u];
                         t[u].x = cell_update(t[u].x, d, rj.x, ci);
                         t[u].y = cell_update(t[u].y, d, rj.y, ci);
                     }
@@ -969,11 +1001,12 @@ update_fused2_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t c
             for (int l = 0; l < f; ++l) {
                 const double2 rj = *reinterpret_cast<const double2 *>(&s_rows[l][2 * tid]);
                 const LevelDiv L = s_lvl[l];
-                const double *cl = s_cols + (int64_t)l * tr + ii;
+                double cv[FUP_UNROLL];                               // tr and ii are multiples of 8: 64-byte aligned
+                load_cols8(cv, s_cols + (int64_t)l * tr + ii);
 #pragma unroll
                 for (int u = 0; u < FUP_UNROLL; ++u) {
                     const int ti = i0 + ii + u;
-                    const double ci = cl[u];
+                    const double ci = cv[u];
                     t[u].x = apply_level(t[u].x, ti, j, L, rj.x, ci);
                     t[u].y = apply_level(t[u].y, ti, j + 1, L, rj.y, ci);
                 }
@@ -1043,7 +1076,8 @@ int64_t fused_workspace_bytes(int n, int64_t ld) { return carve_work(nullptr, n,
 
 int64_t get_option(int key);
 
-// SPX_OPT_FUSE_VARIANT != 0: the experimental update kernel (bit 0: register prefetch of the next batch);
+// SPX_OPT_FUSE_VARIANT != 0: the experimental update kernel (bit 0: register prefetch of the next batch, bit 2:
+// two-instruction guard);
 // SPX_OPT_FUSE_TILE_ROWS: its tile height (0 = 64).  Returns cudaErrorNotSupported when the default kernel is selected.
 static cudaError_t launch_update_variant(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R,
                                          const PlanHeader *plan, const double *ROWS, const double *COLS, int minb,
@@ -1052,27 +1086,31 @@ static cudaError_t launch_update_variant(double *A0, double *A1, int n, int m, i
     if (variant == 0) return cudaErrorNotSupported;
     int tr = (int)get_option(SPX_OPT_FUSE_TILE_ROWS);
     if (tr <= 0) tr = 64;
-    const bool prefetch = (variant & 1) != 0;
+    const bool prefetch = (variant & 1) != 0, guard2 = (variant & 4) != 0;
     const size_t smem = sizeof(double) * FUSE_MAX * (FUP_TC + (size_t)tr);
     static bool configured = false;
     cudaError_t e;
     if (!configured) {
         const int cap = (int)(sizeof(double) * FUSE_MAX * (FUP_TC + 256));
-#define SPX_CFG2(MB, PF) \
-        if ((e = cudaFuncSetAttribute(update_fused2_kernel<MB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
-        SPX_CFG2(2, false) SPX_CFG2(3, false) SPX_CFG2(4, false) SPX_CFG2(2, true) SPX_CFG2(3, true) SPX_CFG2(4, true)
+#define SPX_CFG2(MB, PF, G2) \
+        if ((e = cudaFuncSetAttribute(update_fused2_kernel<MB, PF, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
+#define SPX_CFG2_ALL(PF, G2) SPX_CFG2(2, PF, G2) SPX_CFG2(3, PF, G2) SPX_CFG2(4, PF, G2)
+        SPX_CFG2_ALL(false, false) SPX_CFG2_ALL(true, false) SPX_CFG2_ALL(false, true) SPX_CFG2_ALL(true, true)
+#undef SPX_CFG2_ALL
 #undef SPX_CFG2
         configured = true;
     }
     dim3 grid((unsigned)((m + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + tr - 1) / tr));
     if (grid.x == 0) return cudaSuccess;
-#define SPX_RUN2(MB, PF) \
-    update_fused2_kernel<MB, PF><<<grid, FUP_THREADS, smem, stream>>>(A0, A1, n, m, ld, cbd, col0, R, tr, plan, ROWS, COLS)
-    if (prefetch) {
-        if (minb == 2) SPX_RUN2(2, true); else if (minb == 3) SPX_RUN2(3, true); else SPX_RUN2(4, true);
-    } else {
-        if (minb == 2) SPX_RUN2(2, false); else if (minb == 3) SPX_RUN2(3, false); else SPX_RUN2(4, false);
-    }
+#define SPX_RUN2(MB, PF, G2) \
+    update_fused2_kernel<MB, PF, G2><<<grid, FUP_THREADS, smem, stream>>>(A0, A1, n, m, ld, cbd, col0, R, tr, plan, ROWS, COLS)
+#define SPX_RUN2_MB(PF, G2) \
+    do { if (minb == 2) SPX_RUN2(2, PF, G2); else if (minb == 3) SPX_RUN2(3, PF, G2); else SPX_RUN2(4, PF, G2); } while (0)
+    if (prefetch && guard2) SPX_RUN2_MB(true, true);
+    else if (prefetch) SPX_RUN2_MB(true, false);
+    else if (guard2) SPX_RUN2_MB(false, true);
+    else SPX_RUN2_MB(false, false);
+#undef SPX_RUN2_MB
 #undef SPX_RUN2
     spx_host::count_launch();
     return cudaGetLastError();

@@ -442,7 +442,7 @@ int set_option(int key, int64_t value) {
     case SPX_OPT_FUSE_MIN_BLOCKS:  if (value < 0 || value > 4) return -1; break;
     case SPX_OPT_FUSE_PRICING:     if (value < 0 || value > 2) return -1; break;
     case SPX_OPT_FUSE_LOOKAHEAD:   if (value < 0 || value > 2) return -1; break;
-    case SPX_OPT_FUSE_VARIANT:     if (value < 0 || value > 3) return -1; break;
+    case SPX_OPT_FUSE_VARIANT:     if (value < 0 || value > 7) return -1; break;
     case SPX_OPT_FUSE_TILE_ROWS:   if (value < 0 || value > 256 || value % 8) return -1; break;
     default: return -1;
     }

@@ -86,7 +86,7 @@ def test_options_validate_their_ranges(native):
     try:
         assert L.spx_get_option(10) == 0 and L.spx_get_option(11) == 0 and L.spx_get_option(7) == 0   # defaults
         assert L.spx_set_option(10, 3) == 0 and L.spx_get_option(10) == 3
-        assert L.spx_set_option(10, 4) != 0 and L.spx_set_option(10, -1) != 0
+        assert L.spx_set_option(10, 8) != 0 and L.spx_set_option(10, -1) != 0
         assert L.spx_set_option(11, 40) == 0 and L.spx_get_option(11) == 40
         assert L.spx_set_option(11, 12) != 0 and L.spx_set_option(11, 264) != 0
         assert L.spx_set_option(6, 9) != 0 and L.spx_set_option(99, 0) != 0

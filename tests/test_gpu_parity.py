@@ -708,7 +708,8 @@ def test_column_sharded_ranks_emulated_entering_column_on_late_ranks(spx, world,
 
 # --------------------------------------------------------------------------- experimental fused update kernel
 EXPERIMENTAL = __import__("os").environ.get("SPX_EXPERIMENTAL", "0") == "1"
-X_MODES = ["fused-x2-32", "fused-x2-64", "fused-x2-256", "fused-x3-64-2", "fused-x3-128-2", "fused-x3-40-3", "fused-x3-8"]
+X_MODES = ["fused-x2-32", "fused-x6-64", "fused-x2-256", "fused-x3-64-2", "fused-x7-128-2", "fused-x7-40-3", "fused-x3-8",
+           "fused-x6-32-4"]
 
 
 @pytest.mark.skipif(not EXPERIMENTAL, reason="update_fused2_kernel (SPX_OPT_FUSE_VARIANT) was written after round 1's GPU "

@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--minb", default="3")
     ap.add_argument("--variants", default="0",
                     help="update kernel schedules as variant:tile_rows, e.g. 0,2:64,3:64,3:128 (0 = the default kernel; "
-                         "2 / 3 = the experimental kernel without / with register prefetch)")
+                         "experimental kernel: 2, +1 register prefetch, +4 two-instruction guard)")
     a = ap.parse_args()
     L = N.lib()
     rows, c = W.dense_lp(a.n, a.m, 0)

@@ -22,7 +22,7 @@ SPX_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu 
     > "$out/experimental_update.log" 2>&1
 echo "experimental fused update kernel (bit-exactness): exit $?" | tee -a "$out/summary.txt"
 timeout 420 python tools/fused_lab.py --pivots 400 --depths 8 --minb 2,3,4 \
-    --variants 0,2:32,2:64,2:128,3:64,3:128,3:256 > "$out/fused_lab_variants.log" 2>&1
+    --variants 0,2:32,6:32,6:64,6:128,7:64,7:128,7:256 > "$out/fused_lab_variants.log" 2>&1
 echo "fused_lab variant sweep: exit $?" | tee -a "$out/summary.txt"
 timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
     --master-port 29517 bench.py --gpus 2 --steps 2 --warmup 3 --no-batched > "$out/bench_n2.log" 2>&1
