@@ -185,6 +185,22 @@ def test_oracle_pick_update_equal_live_reference_medium(reference_module):
         assert np.array_equal(bits(got), bits(T))
 
 
+@pytest.mark.parametrize("n,m,cap,kind", [(24, 200, 40, "late"), (40, 400, 64, "late"), (20, 160, 30, "late"),
+                                          (12, 300, 30, "smallint")])
+def test_oracle_equals_live_reference_on_the_sharded_test_lps(reference_module, n, m, cap, kind):
+    """The LP families the sharded-flow tests use (util.make_lp: entering column on the LAST column block and
+    moving between blocks; degenerate small integers) through the reference itself, so the oracle those tests
+    compare against is pinned on exactly this kind of input too."""
+    from util import make_lp
+    rows, c = make_lp(n, m, 7, kind)
+    end, trace, flat, rl, cl = _drive_reference(reference_module, rows, c, cap)
+    o = oracle.solve(rows, c, max_pivots=cap)
+    assert o.status == END_TO_STATUS[end]
+    assert o.trace.tolist() == trace and len(trace) >= 10
+    assert np.array_equal(bits(o.table), bits(flat))
+    assert oracle.label_strings(o.rowlab, o.collab, m) == (rl, cl)
+
+
 def test_golden_file_provenance(ref_cases):
     names = [c["name"] for c in ref_cases]
     assert len(set(names)) == len(names)
