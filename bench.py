@@ -621,7 +621,9 @@ def run_ours(args):
                            **({"exchange_fallback": fallback_note} if fallback_note else {})),
             "clocks": clk.summary(),
             "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "update_kernel (K3), whole step incl. exchange",
+            "roofline": {"bound": "hbm",
+                         "kernel": ("update_fused_kernel (K6)" if args.exchange == "fused" else "update_tiled_kernel (K3)") +
+                                   ": WHOLE step incl. pricing and exchange, 16 B x cells per pivot / step time / N",
                          "achieved": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9 / world,
                          "peak": peak, "unit": "GB/s per GPU", "peak_source": peak_src,
                          "frac": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9 / world / peak,
