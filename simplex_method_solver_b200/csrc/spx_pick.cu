@@ -94,7 +94,10 @@ __device__ void block_entering(const double *__restrict__ A, const double *__res
 //   npiv/cap   : pivots applied to the table being priced / max_pivots
 struct Decision { int status; int r; double p; };
 
-__device__ Decision block_decide(const double *__restrict__ col, int64_t stride,
+// col may point into a peer mailbox that remote GPUs wrote while this kernel was already resident
+// (shard_select_kernel / ahead_select_kernel): no __restrict__ and explicit ld.global.cg reads, so the
+// compiler can never turn them into non-coherent ld.global.nc loads that the flag acquire does not order.
+__device__ Decision block_decide(const double *col, int64_t stride,
                                  const double *__restrict__ b, int n, int r1, int64_t cglob,
                                  int64_t npiv, int64_t cap, double *__restrict__ colbuf, Scratch &s) {
     Decision dec; dec.r = -1; dec.p = 0.0;
@@ -110,7 +113,7 @@ __device__ Decision block_decide(const double *__restrict__ col, int64_t stride,
 #pragma unroll
         for (int u = 0; u < GATHER_BATCH; ++u) {
             const int i = base + u * nt + (int)threadIdx.x;
-            a[u]  = (i <= n) ? col[(int64_t)i * stride] : 0.0;
+            a[u]  = (i <= n) ? __ldcg(col + (int64_t)i * stride) : 0.0;
             bb[u] = (r1 < 0 && i < n) ? b[i] : 0.0;
         }
 #pragma unroll
@@ -129,7 +132,7 @@ __device__ Decision block_decide(const double *__restrict__ col, int64_t stride,
         q = block_ratio_reduce(q, s);
         bool elig_nan = false;
         if (q.elig_row != SPX_NONE) {
-            const double v = __ddiv_rn(b[q.elig_row], col[(int64_t)q.elig_row * stride]);
+            const double v = __ddiv_rn(b[q.elig_row], __ldcg(col + (int64_t)q.elig_row * stride));
             elig_nan = (v != v);
         }
         r = ratio_decide(q, elig_nan);                                 // :138-141
@@ -137,7 +140,7 @@ __device__ Decision block_decide(const double *__restrict__ col, int64_t stride,
     dec.status = (r < 0) ? SPX_NOCONV : SPX_PIVOT;
     if (dec.status == SPX_PIVOT) {
         dec.r = r;
-        dec.p = col[(int64_t)r * stride];
+        dec.p = __ldcg(col + (int64_t)r * stride);
         if (npiv >= cap) dec.status = SPX_CAP;
     }
     return dec;
@@ -145,7 +148,7 @@ __device__ Decision block_decide(const double *__restrict__ col, int64_t stride,
 
 // in-place bookkeeping of the step API (spx_pick / spx_shard_select): the update that follows
 // increments npiv and fills the hint slot
-__device__ void block_finish(const double *__restrict__ col, int64_t stride,
+__device__ void block_finish(const double *col, int64_t stride,
                              const double *__restrict__ b, int n, int r1, int64_t cglob,
                              spx_state *st, double *__restrict__ colbuf, Scratch &s) {
     const Decision dec = block_decide(col, stride, b, n, r1, cglob, st->npiv, st->max_pivots, colbuf, s);

@@ -120,3 +120,32 @@ def snapshot_digest(tables) -> str:
             for v in row:
                 h.update(struct.pack("<d", float(v)))
     return h.hexdigest()
+
+
+def body_checksum_numpy(body: np.ndarray) -> int:
+    """Order-free 64-bit checksum of an [n, m] fp64 body (a strided view is fine):
+    sum of bits(T[i][j]) * (2*(i*m + j) + 1) mod 2^64.  Sensitive to every bit of every cell
+    (the weight is odd), cheap enough for 4.3 GB tables on both sides of the comparison."""
+    n, m = body.shape
+    acc = np.uint64(0)
+    j2 = (np.arange(m, dtype=np.uint64) << np.uint64(1)) + np.uint64(1)
+    with np.errstate(over="ignore"):
+        for i0 in range(0, n, 256):
+            blk = np.ascontiguousarray(body[i0:i0 + 256]).view(np.uint64)
+            base = (np.arange(i0, i0 + blk.shape[0], dtype=np.uint64) * np.uint64(2 * m))[:, None]
+            acc = acc + (blk * (base + j2[None, :])).sum(dtype=np.uint64)
+    return int(acc)
+
+
+def body_checksum_torch(body) -> int:
+    """Same checksum for a device tensor view [n, m] (fp64, any row stride); int64 wraps mod 2^64."""
+    import torch
+    n, m = body.shape
+    dev = body.device
+    j2 = torch.arange(m, dtype=torch.int64, device=dev) * 2 + 1
+    acc = torch.zeros((), dtype=torch.int64, device=dev)
+    for i0 in range(0, n, 1024):
+        blk = body[i0:i0 + 1024].contiguous().view(torch.int64)
+        base = (torch.arange(i0, i0 + blk.shape[0], dtype=torch.int64, device=dev) * (2 * m))[:, None]
+        acc = acc + (blk * (base + j2[None, :])).sum()
+    return int(acc.item()) & 0xFFFFFFFFFFFFFFFF

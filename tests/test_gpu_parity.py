@@ -51,7 +51,8 @@ class loop_mode:
 @pytest.fixture(scope="module")
 def spx():
     import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    if not torch.cuda.is_available():
+        pytest.skip("GPU tests need a CUDA device")
     from simplex_method_solver_b200 import _native, batched, engine, simplex
     _native.lib()
 

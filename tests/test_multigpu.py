@@ -63,12 +63,9 @@ def _worker(rank, world, port, n, m, seed, cap, mode, kind, out):
         dist.destroy_process_group()
 
 
-# The "smallint" (degenerate ties, phase-1 pivots) and "late" (entering columns on the LAST ranks) cases
-# were added at the very end of round 1: their first run on 2 GPUs hit the old harness's hang-on-failure
-# and used up the round's GPU budget before the outcome could be read, and the race that most likely
-# caused it (COL planes overwritten under a slow rank's update, fixed by triple-buffering them) could
-# not be re-verified on hardware.  They run with SPX_MULTIGPU_EXTENDED=1 — the first thing to do in round 2.
-EXTENDED = os.environ.get("SPX_MULTIGPU_EXTENDED", "0") == "1"
+# The "smallint" (degenerate ties, phase-1 pivots) and "late" (entering columns on the LAST ranks, ~30-60 owner
+# changes) cases exercise the winner != rank 0 branch of every exchange.  First hardware run: round 2, 2 x B200,
+# all four exchange modes green (profiles/r2/r2a_multigpu_extended_2gpu_summary.txt); they are no longer gated.
 
 
 @pytest.mark.parametrize("mode", ["fused", "p2p", "nccl", "nccl-ahead"])
@@ -79,8 +76,6 @@ EXTENDED = os.environ.get("SPX_MULTIGPU_EXTENDED", "0") == "1"
                                           (64, 1600, 100, "late")])         # owners 19/3/41/37 at world 4
 def test_sharded_flow_on_real_gpus(mode, n, m, cap, kind):
     import torch
-    if kind != "dense" and not EXTENDED:
-        pytest.skip("extended multi-GPU case: set SPX_MULTIGPU_EXTENDED=1 (see the note above)")
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
