@@ -98,11 +98,12 @@ int64_t     spx_launch_count(int reset);
 #define SPX_OPT_PIPE_GRID        4  /* pipelined kernel CTAs (0 = one per SM) */
 #define SPX_OPT_TILED_ROWS       5  /* tiled kernel rows per tile (0 = auto; else a multiple of 8 <= 64) */
 #define SPX_OPT_FUSE_DEPTH       6  /* fused loop: pivots applied per pass over the body (0 = default 8, max 8) */
-#define SPX_OPT_FUSE_MIN_BLOCKS  7  /* fused update kernel: resident CTAs per SM its register budget targets (2..4, 0 = default 4) */
+#define SPX_OPT_FUSE_MIN_BLOCKS  7  /* fused update kernel: resident CTAs per SM its register budget targets (2..4, 0 = default 3) */
 #define SPX_OPT_FUSE_PRICING     8  /* fused loop pricing kernel: 0 auto, 1 one CTA, 2 whole-GPU cooperative */
 #define SPX_OPT_FUSE_LOOKAHEAD   9  /* fused loop in spx_solve: 1 = price pass q+1 on a side stream during update q (default 0: off on one GPU) */
-#define SPX_OPT_FUSE_VARIANT     10 /* fused update kernel: 0 default; EXPERIMENTAL (bits): 2 = runtime tile height + per-warp slow path, +1 = register prefetch of the next batch, +4 = two-instruction range guard */
-#define SPX_OPT_FUSE_TILE_ROWS   11 /* experimental fused update kernel: rows per tile (0 = 64; a multiple of 8 <= 256) */
+#define SPX_OPT_FUSE_VARIANT     10 /* fused update kernel: 0 default (lazy range guard: one range test per cell per PASS), 1 = round 1's kernel (range test per cell per level) */
+#define SPX_OPT_FUSE_TILE_ROWS   11 /* fused update kernel: rows per item (0 = 32; a multiple of 8 <= 256) */
+#define SPX_OPT_FUSE_ITEMS       12 /* fused update kernel: 64-column x TILE_ROWS items per warp (0 = 8; 1..64) */
 int         spx_set_option(int32_t option, int64_t value);
 int64_t     spx_get_option(int32_t option);
 /* Device self-test of the hoisted-reciprocal division used by K3 against the
@@ -110,6 +111,15 @@ int64_t     spx_get_option(int32_t option);
  * number of bit mismatches in *h_mismatches (and the first offending pair). */
 int         spx_selftest_division(const double *d_a, const double *d_p, int64_t count, int64_t np,
                                   uint64_t *h_mismatches, double *h_first_bad, void *stream);
+/* Device self-test of the fused update's LAZY range guard (csrc/spx_fused.cu, update_lazy_kernel): chain k < count
+ * takes the cell d_t0[k] through `levels` (1..8) pending pivots — pivot values d_p[levels], pivot-row values
+ * d_rj[count][levels], pivot-column values d_ci[count][levels], i.e. `levels` applications of
+ * recalculate_matrix()'s cell formula (simplex.py:173-175) — once the kernel's way (unguarded fast divisions, ONE
+ * range test on the result, guarded re-do when it fails) into d_out_lazy, once with every division guarded into
+ * d_out_ref.  The caller compares the bits.  *h_redo = how many chains took the re-do. */
+int         spx_selftest_lazy_guard(const double *d_t0, const double *d_p, const double *d_rj, const double *d_ci,
+                                    int32_t levels, int64_t count, double *d_out_lazy, double *d_out_ref,
+                                    uint64_t *h_redo, void *stream);
 
 /* ---- layout conversion (SimplexMethod.__init__, simplex.py:25-39) -------- */
 /* src_rows is the reference's `constraints` as a dense row-major [n][m+1] fp64

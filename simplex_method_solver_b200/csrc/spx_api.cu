@@ -42,6 +42,8 @@ int64_t get_option(int);
 int     set_option(int, int64_t);
 cudaError_t selftest_division(const double *, const double *, int64_t, int64_t, unsigned long long *,
                               double *, cudaStream_t);
+cudaError_t lazy_guard_selftest(const double *, const double *, const double *, const double *, int, int64_t,
+                                double *, double *, unsigned long long *, cudaStream_t);
 cudaError_t init_state(spx_state *, int32_t *, int32_t *, int, int, int64_t, cudaStream_t);
 cudaError_t solve_batched(double *, int64_t, int, int, int, int, double *, double *, int32_t *,
                           int32_t *, int32_t *, int32_t *, int32_t *, double *, cudaStream_t);
@@ -150,6 +152,26 @@ int spx_selftest_division(const double *d_a, const double *d_p, int64_t count, i
     cudaFree(d_bad);
     *h_mismatches = cnt;
     if (h_first_bad) { h_first_bad[0] = bad[0]; h_first_bad[1] = bad[1]; }
+    return rc;
+}
+
+int spx_selftest_lazy_guard(const double *d_t0, const double *d_p, const double *d_rj, const double *d_ci,
+                            int32_t levels, int64_t count, double *d_out_lazy, double *d_out_ref,
+                            uint64_t *h_redo, void *stream) {
+    SPX_REQUIRE(d_t0 && d_p && d_rj && d_ci && d_out_lazy && d_out_ref && h_redo && count >= 0 && levels >= 1 &&
+                levels <= spx_launch::fuse_max(), "spx_selftest_lazy_guard: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    unsigned long long *d_cnt = nullptr, cnt = 0;
+    if (check(cudaMalloc(&d_cnt, sizeof(*d_cnt)), "cudaMalloc")) return -1;
+    int rc = 0;
+    if (check(cudaMemsetAsync(d_cnt, 0, sizeof(*d_cnt), s), "memset") ||
+        check(spx_launch::lazy_guard_selftest(d_t0, d_p, d_rj, d_ci, levels, count, d_out_lazy, d_out_ref, d_cnt, s),
+              "selftest launch") ||
+        check(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, s), "read") ||
+        check(cudaStreamSynchronize(s), "sync"))
+        rc = -1;
+    cudaFree(d_cnt);
+    *h_redo = cnt;
     return rc;
 }
 

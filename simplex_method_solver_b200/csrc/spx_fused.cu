@@ -854,29 +854,55 @@ update_fused_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cb
     }
 }
 
-// ---- EXPERIMENTAL variant of the fused update (selected with SPX_OPT_FUSE_VARIANT != 0; not the default,
-// written after round 1's GPU budget was spent — see DESIGN.md "What comes next", item 2).  Same arithmetic
-// and the same bits as update_fused_kernel; what changes is the schedule:
-//   * tile height `tr` is a runtime value (SPX_OPT_FUSE_TILE_ROWS: 32..256): the 8 ROW slices of a column
-//     tile and the staging barrier are paid once per tr rows instead of once per 32;
-//   * PREFETCH: the next 8-row batch is loaded into a second register set before the current one is
-//     computed, so a warp always has 8 x 512 B of its own reads in flight;
-//   * the slow path (apply_level with its row / column tests) is taken per 8-row batch and per WARP — a
-//     batch that holds a pivot row, or a warp whose 64 columns hold a pivot column — instead of per tile;
-//   * GUARD2: the accumulated range test of pivot_div_unchecked, qlo <= (hi & 0x7fffffff) <= 0x7f800000, as
-//     ONE subtraction and ONE unsigned compare per quotient: doubling hi drops the sign bit, so the test is
-//     (2 * hi - 2 * qlo) mod 2^32 < 0xff000001 - 2 * qlo  (and "< 0", never true, when qlo is the
-//     always-fail sentinel 0x7f800001).
-__device__ __forceinline__ double cell_update_guard2(double t, const PivotDiv &d, double rj, double ci,
-                                                     unsigned q2, unsigned qr, bool &ok) {
-    const double a   = __dsub_rn(__dmul_rn(t, d.p), __dmul_rn(rj, ci));
-    const double q0  = __dmul_rn(a, d.y);
-    const double rem = __fma_rn(-d.p, q0, a);
-    const double q1  = __fma_rn(d.y, rem, q0);
-    unsigned tdiff;                                                 // 2 * hi - 2 * qlo in ONE instruction (IMAD)
-    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(tdiff) : "r"((unsigned)__double2hiint(q1)), "r"(0u - q2));
-    ok = ok && (tdiff < qr);
-    return q1;
+// ---- K6b: the fused update with the LAZY range guard (the default; SPX_OPT_FUSE_VARIANT = 1 selects the
+// round-1 kernel above).  Same arithmetic, same bits; what changed is what the steady state pays per cell-level.
+//
+// Round 1's kernel spent 3 integer instructions per quotient on the accumulated range test of
+// pivot_div_unchecked.  Measured on a B200 with everything in registers (tools/fp64_lab.cu,
+// profiles/r2/r2c_fp64_lab.log): the bare 6-instruction fp64 chain holds the fp64 pipe at 92 %, the chain plus
+// that guard at 78 %, plus a one-instruction-per-two-cells FMNMX3 guard at 82 % — the guard, not latency, was the
+// gap (the register-prefetch / tall-tile schedules of round 1's experimental kernel measured no faster,
+// profiles/r2/r2b_fused_update_variant_sweep.log, and are gone).  Here the per-level guard is GONE:
+//
+//   the fast division (q0 = a*y; rem = fma(-p, q0, a); q = fma(y, rem, q0), y the correctly rounded reciprocal)
+//   returns RN(a / p) unless (i) a, q0 or q overflow — then q is Inf/NaN, and Inf/NaN stay Inf/NaN through every
+//   later level — or (ii) |a| < 2^-969 or q is subnormal (rem or q underflow, or a = +-0 whose quotient gets the
+//   wrong SIGN of zero).  In case (ii) the computed q~ and the true q are both tiny: |q|, |q~| <= 2^-969 / |p|.
+//   Let every pivot of the pass satisfy 2^-100 <= |p| <= 2^100 (checked per tile; otherwise the guarded path
+//   runs).  A pair (q~, q) with |q|, |q~| <= B entering the next level gives a = RN(RN(t p') - rc): either
+//   |rc| >= 2^54 B |p'|, then t p' is absorbed entirely, a~ = a = -rc and the error is gone; or |rc| is smaller,
+//   then |a|, |a~| < 2^55 B |p'| and the pair stays small with B' = 2^55 B.  Starting from B = 2^-869, seven more
+//   levels give B <= 2^-484.  So a value that differs from the reference's is, at the END of the pass, either
+//   Inf/NaN or smaller than 2^-484 in magnitude: ONE range test on the outputs, 2^-400 <= |q| < 2^1009, proves
+//   all FUSE_MAX levels of a cell exact.  A thread whose batch fails it re-does the batch from the stored cells
+//   with the fully guarded division (exact zeros — sparse tableaus — take that road, as they did in round 1).
+//   spx_selftest_lazy_guard() runs adversarial chains (zeros, subnormals, cancellation to 2^-1000, Inf) through
+//   both paths on the device and compares bits; tests/test_gpu_parity.py calls it.
+//
+// The test itself is two FMNMX3 per two outputs on the sign-stripped HIGH WORDS read as fp32 (monotonic in the
+// fp64 magnitude; max.NaN keeps the NaN pattern of exponents >= 2040): 16 instructions per 768 fp64 issues.
+// Other changes: the level loop is fully unrolled for a full pass (f == FUSE_MAX); (p, y) of a level is one
+// 128-bit shared load, the 8 column multipliers four; the slow path (pivot row / pivot column inside the batch)
+// is taken per 8-row batch and per warp instead of per tile; the first batch's loads are issued before the CTA
+// waits for its staged slices.
+constexpr unsigned LZ_LOW  = (unsigned)(1023 - 400) << 20;     // outputs below 2^-400 are re-done exactly
+constexpr unsigned LZ_HIGH = 0x7f000000u;                      // ... and so are |q| >= 2^1009, Inf, NaN
+constexpr int      LZ_P_SPAN = 100;                            // lazy guard only if 2^-100 <= |p| <= 2^100
+
+__device__ __forceinline__ double cell_update_raw(double t, double p, double y, double rj, double ci) {
+    const double a   = __dsub_rn(__dmul_rn(t, p), __dmul_rn(rj, ci));      // :173-175, three roundings
+    const double q0  = __dmul_rn(a, y);
+    const double rem = __fma_rn(-p, q0, a);
+    return __fma_rn(y, rem, q0);
+}
+
+__device__ __forceinline__ void range_fold(float &lo, float &hi, double x, double y) {
+    const float fx = fabsf(__int_as_float(__double2hiint(x))), fy = fabsf(__int_as_float(__double2hiint(y)));
+    asm("min.f32 %0, %0, %1, %2;" : "+f"(lo) : "f"(fx), "f"(fy));                  // FMNMX3
+    asm("max.NaN.f32 %0, %0, %1, %2;" : "+f"(hi) : "f"(fx), "f"(fy));              // FMNMX3.NAN
+}
+__device__ __forceinline__ bool range_ok(float lo, float hi) {
+    return __float_as_uint(lo) >= LZ_LOW && __float_as_uint(hi) <= LZ_HIGH;
 }
 
 __device__ __forceinline__ void load_cols8(double (&cv)[FUP_UNROLL], const double *p) {
@@ -886,144 +912,276 @@ __device__ __forceinline__ void load_cols8(double (&cv)[FUP_UNROLL], const doubl
     for (int u = 0; u < 4; ++u) { const double2 v = p2[u]; cv[2 * u] = v.x; cv[2 * u + 1] = v.y; }
 }
 
-template <int MINB, bool PREFETCH, bool GUARD2>
+// one level on a thread's 8 x 2 cells, no guard
+__device__ __forceinline__ void lazy_level(double2 (&t)[FUP_UNROLL], const double2 rj, const double2 py, const double *cols) {
+    double cv[FUP_UNROLL];
+    load_cols8(cv, cols);
+#pragma unroll
+    for (int u = 0; u < FUP_UNROLL; ++u) {
+        t[u].x = cell_update_raw(t[u].x, py.x, py.y, rj.x, cv[u]);
+        t[u].y = cell_update_raw(t[u].y, py.x, py.y, rj.y, cv[u]);
+    }
+}
+
+// the rare road: a batch that holds a pivot row / column, failed the range test or is ragged — the reference's
+// formulas with the fully guarded division (pivot row :156, pivot column :160, pivot cell :163, ordinary cells
+// :173-175), one row pair per call.  Not inlined and by value: neither its registers nor an addressable copy of the
+// batch may weigh on the steady state.
+__device__ __noinline__ double2 guarded_pair(double2 t, int f, const LevelDiv *s_lvl, const double *s_rows, int lane,
+                                             const double *col, int tr, int row, int j) {
+    for (int l = 0; l < f; ++l) {
+        const double2 rj = *reinterpret_cast<const double2 *>(s_rows + l * 64 + 2 * lane);
+        const LevelDiv L = s_lvl[l];
+        const double ci = col[l * tr];
+        t.x = apply_level(t.x, row, j, L, rj.x, ci);
+        t.y = apply_level(t.y, row, j + 1, L, rj.y, ci);
+    }
+    return t;
+}
+
+// WARP-AUTONOMOUS: there is no CTA-wide barrier, no mbarrier and no elected producer in this kernel.  An item is a
+// 64-column strip x tr rows; warp w of CTA b owns the `items` consecutive items (b * 8 + w) * items ... (adjacent
+// strips of the same row tile, so a CTA covers 8 * items * 64 contiguous columns).  Each warp keeps ITS OWN slices
+// in shared memory: every lane loads the 8 ROW_l values of ITS two columns with 128-bit loads and parks them in
+// its own shared-memory slot (nobody else reads them: no synchronisation), and the 8 x tr COL_l multipliers of the
+// row tile are copied cooperatively when the row tile changes (one __syncwarp).  These loads are issued together
+// with the first 8 rows of the item, so their latency hides behind the global loads the warp waits for anyway.
+// Why not CTA-wide TMA staging as in K3 / round 1's kernel: measured (profiles/r2/), (i) with CTA-wide staging the
+// warps of all co-resident CTAs moved in lock step — prologue barrier + TMA round trip together, hot loops
+// together — and the fp64 pipe idled ~25 % of the time although 2.6 warps per scheduler were ready on average;
+// (ii) the dispatch port is the binding resource: an fp64 warp instruction holds it for 2 cycles, any other for 1
+// (tools/fp64_lab.cu reproduces every measured pipe utilisation with that model), so every instruction that is not
+// one of the 6 fp64 issues per cell-level costs fp64 throughput — the elected-lane cp.async.bulk loops (16 copies
+// per item) and the mbarrier polling were ~1/3 of the non-fp64 instructions.
+constexpr int LZ_SC = 64;                       // columns per strip (2 per lane)
+
+struct LazyWarpSmem {                           // static shared memory of one warp
+    LevelDiv lvl[FUSE_MAX];
+    double2  py[FUSE_MAX];                      // (p, y) per level: one 128-bit load
+    int      guarded;                           // some pivot of the pass is outside the lazy guard's span
+    int      pad[3];
+};
+
+template <int MINB>
 __global__ void __launch_bounds__(FUP_THREADS, MINB)
-update_fused2_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R, int tr,
-                     const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
-                     const double *__restrict__ COLS) {
+update_lazy_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R, int tr, int items,
+                   const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
+                   const double *__restrict__ COLS) {
     const int f = plan->f;
     if (f <= 0) return;
-    extern __shared__ __align__(128) unsigned char fus2_raw[];
-    double (*s_rows)[FUP_TC] = reinterpret_cast<double (*)[FUP_TC]>(fus2_raw);          // [FUSE_MAX][FUP_TC]
-    double *s_cols = reinterpret_cast<double *>(fus2_raw + sizeof(double) * FUSE_MAX * FUP_TC);   // [FUSE_MAX][tr]
-    __shared__ LevelDiv s_lvl[FUSE_MAX];
-    __shared__ alignas(8) uint64_t s_bar;
+    extern __shared__ __align__(128) unsigned char lz_raw[];
+    __shared__ __align__(16) LazyWarpSmem s_w[FUP_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    LazyWarpSmem &W = s_w[warp];
+    double *s_rows = reinterpret_cast<double *>(lz_raw + (size_t)warp * sizeof(double) * FUSE_MAX * (LZ_SC + tr));   // [FUSE_MAX][64]
+    double *s_cols = s_rows + FUSE_MAX * LZ_SC;                                                                     // [FUSE_MAX][tr]
 
     const int src = plan->src;
     const double *__restrict__ Ain = src ? A1 : A0;
     double *__restrict__ Aout = src ? A0 : A1;
 
-    const int tid = threadIdx.x;
-    const int j0 = blockIdx.x * FUP_TC;
-    const int i0 = blockIdx.y * tr;
-    const int rows = min(tr, n + 1 - i0);
-    const uint32_t row_bytes = (uint32_t)(min((int64_t)FUP_TC, ld - j0) * 8);
-    const uint32_t col_bytes = (uint32_t)(min((int64_t)tr, cbd - i0) * 8);            // planes hold cbd >= n + 1 cells
-    if (tid == 0) {
-        mbar_init(&s_bar, 1);
-        mbar_fence_init();
-        mbar_expect_tx(&s_bar, (uint32_t)f * (row_bytes + col_bytes));
-        for (int l = 0; l < f; ++l) {
-            bulk_g2s(s_rows[l], ROWS + (int64_t)l * ld + j0, row_bytes, &s_bar);
-            bulk_g2s(s_cols + (int64_t)l * tr, COLS + ((int64_t)l * R + plan->owner[l]) * cbd + i0, col_bytes, &s_bar);
+    const int nstrips = (m + LZ_SC - 1) / LZ_SC;
+    const int nrt = (n + 1 + tr - 1) / tr;
+    const int nitems = nstrips * nrt;                           // < 2^31: checked by the launcher
+    const int first = (blockIdx.x * (FUP_THREADS / 32) + warp) * items;
+    if (first >= nitems) return;
+    const int last = min(first + items, nitems) - 1;
+
+    // ---- once per warp: the levels (the same for every item); does any pivot row / column touch this warp's items?
+    if (lane == 0) W.guarded = 0;
+    __syncwarp();
+    bool touch = false;
+    if (lane < f) {
+        const double p = plan->lvl[lane].p;
+        const int rl = plan->lvl[lane].r;
+        W.lvl[lane].r = rl;
+        const int64_t cg = (int64_t)plan->lvl[lane].c - col0;       // the plan carries GLOBAL column indices
+        const int cl = (cg >= 0 && cg < m) ? (int)cg : -1;
+        W.lvl[lane].c = cl;
+        const PivotDiv d = pivot_div_prepare(p);
+        W.lvl[lane].d = d;
+        W.py[lane] = make_double2(d.p, d.y);
+        const int ep = (__double2hiint(p) >> 20) & 0x7ff;
+        if (!d.ok || ep < 1023 - LZ_P_SPAN || ep > 1023 + LZ_P_SPAN) W.guarded = 1;
+        // items first..last cover row tiles first / nstrips .. last / nstrips; a pivot row in one of them, or (one row
+        // tile only) a pivot column in one of the strips, or (several row tiles) any local pivot column
+        const int rt0 = first / nstrips, rt1 = last / nstrips;
+        const int prt = rl / tr;
+        touch = prt >= rt0 && prt <= rt1;
+        if (cl >= 0) {
+            const int ps = cl / LZ_SC;
+            touch = touch || rt1 > rt0 || (ps >= first - rt0 * nstrips && ps <= last - rt0 * nstrips);
         }
     }
-    if (tid < f) {
-        s_lvl[tid].r = plan->lvl[tid].r;
-        const int64_t cl = (int64_t)plan->lvl[tid].c - col0;
-        s_lvl[tid].c = (cl >= 0 && cl < m) ? (int)cl : -1;
-        s_lvl[tid].d = pivot_div_prepare(plan->lvl[tid].p);
-    }
-    __syncthreads();
+    touch = __any_sync(0xffffffffu, touch);
+    __syncwarp();
 
-    const int j = j0 + 2 * tid;
-    const bool active = j < m;
-    const double *srcp = Ain + (int64_t)i0 * ld + j;
-    double *dstp = Aout + (int64_t)i0 * ld + j;
-    double2 t[FUP_UNROLL], tn[FUP_UNROLL];
-    // the first batch does not depend on the staged slices: issue it before waiting for them
+    // row pitch in bytes fits 32 bits (ld <= 2^28 doubles): every row address is ONE IMAD.WIDE.U32 off the batch base
+    const uint32_t ldb = (uint32_t)(ld * 8);
+    const int64_t delta = reinterpret_cast<const char *>(Aout) - reinterpret_cast<const char *>(Ain);
+    // L2 prefetch of the batch after the one in registers: lane L touches 128-byte line (L & 3) of row (L >> 2);
+    // the per-lane offset from this thread's batch base fits 32 bits for ld < 2^24 doubles (else: no prefetch)
+    const uint32_t pfo = ldb * (uint32_t)(FUP_UNROLL + (lane >> 2)) + 128u * (lane & 3) - 16u * lane;
+    const bool pf_ok = ld < (1 << 24);
+    const uint32_t guarded_all = W.guarded ? 0xffffffffu : 0u;
+    double2 *my_rows = reinterpret_cast<double2 *>(s_rows) + lane;                       // level l: my_rows[l * 32]
+
+    int rt = first / nstrips, strip = first - rt * nstrips, rt_staged = -1;
+    for (int it = first; it <= last; ++it) {
+        const int j0 = strip * LZ_SC, i0 = rt * tr;
+        const int rows = min(tr, n + 1 - i0);
+        const int full = rows & ~(FUP_UNROLL - 1);                                        // rows in whole batches
+        const bool active = j0 + 2 * lane < m;
+        const char *sp = reinterpret_cast<const char *>(Ain + (int64_t)i0 * ld + j0 + 2 * lane);  // this lane's pair, first row
+        double2 t[FUP_UNROLL];
+        // the first batch, this lane's 8 ROW values and (new row tile) the COL multipliers: all in flight together
+        if (active && full > 0) {
 #pragma unroll
-    for (int u = 0; u < FUP_UNROLL; ++u)
-        t[u] = (active && u < rows) ? ld_stream(srcp + (int64_t)u * ld) : make_double2(1.0, 1.0);
-    mbar_wait(&s_bar, 0);
-    if (!active) return;
-
-    // warp-uniform: does a pivot column of any level fall into this warp's 64 columns?
-    const int wj0 = j0 + 64 * (tid >> 5);
-    bool colspecial = false;
-    for (int l = 0; l < f; ++l) {
-        const int cl = s_lvl[l].c;
-        colspecial = colspecial || (cl >= wj0 && cl < wj0 + 64);
-    }
-
-    for (int ii = 0; ii < rows; ii += FUP_UNROLL) {
-        if (PREFETCH) {
+            for (int u = 0; u < FUP_UNROLL; ++u) t[u] = ld_stream(reinterpret_cast<const double *>(sp + (uint64_t)ldb * u));
+        }
+        if (active) {
+            const double *rp = ROWS + j0 + 2 * lane;
+            if (f == FUSE_MAX) {
 #pragma unroll
-            for (int u = 0; u < FUP_UNROLL; ++u)
-                tn[u] = (ii + FUP_UNROLL + u < rows) ? ld_stream(srcp + (int64_t)(ii + FUP_UNROLL + u) * ld)
-                                                     : make_double2(1.0, 1.0);
+                for (int h = 0; h < FUSE_MAX; h += 4) {
+                    double2 rv[4];
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) rv[l] = __ldg(reinterpret_cast<const double2 *>(rp + (int64_t)(h + l) * ld));
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) my_rows[(h + l) * (LZ_SC / 2)] = rv[l];
+                }
+            } else {
+                for (int l = 0; l < f; ++l) my_rows[l * (LZ_SC / 2)] = __ldg(reinterpret_cast<const double2 *>(rp + (int64_t)l * ld));
+            }
         }
-        bool special = colspecial;
-        for (int l = 0; l < f; ++l) {
-            const int rl = s_lvl[l].r;
-            special = special || (rl >= i0 + ii && rl < i0 + ii + FUP_UNROLL);
-        }
-        if (!special) {
-            bool ok = true;
+        if (rt != rt_staged) {
+            __syncwarp();                                        // every lane is done with the previous row tile's multipliers
+            const int ncol = (int)min((int64_t)tr, cbd - i0);    // planes hold cbd >= n + 1 cells
             for (int l = 0; l < f; ++l) {
-                const double2 rj = *reinterpret_cast<const double2 *>(&s_rows[l][2 * tid]);
-                const PivotDiv d = s_lvl[l].d;
-                double cv[FUP_UNROLL];                               // tr and ii are multiples of 8: 64-byte aligned
-                load_cols8(cv, s_cols + (int64_t)l * tr + ii);
-                const unsigned q2 = d.qlo + d.qlo;                                   // qlo <= 0x7f800001: no overflow
-                const unsigned qr = (d.qlo > 0x7f800000u) ? 0u : 0xff000001u - q2;
-#pragma unroll
-                for (int u = 0; u < FUP_UNROLL; ++u) {
-                    const double ci = cv[u];
-                    if (GUARD2) {
-                        t[u].x = cell_update_guard2(t[u].x, d, rj.x, ci, q2, qr, ok);
-                        t[u].y = cell_update_guard2(t[u].y, d, rj.y, ci, q2, qr, ok);
-                    } else {
-                        t[u].x = cell_update_unchecked(t[u].x, d, rj.x, ci, ok);
-                        t[u].y = cell_update_unchecked(t[u].y, d, rj.y, ci, ok);
-                    }
+                const double *cp = COLS + ((int64_t)l * R + plan->owner[l]) * cbd + i0;
+                for (int u = lane; u < ncol; u += 32) s_cols[l * tr + u] = __ldcg(cp + u);
+            }
+            __syncwarp();
+            rt_staged = rt;
+        }
+        if (active) {
+            // bit b of slow: batch b takes the guarded road — a pivot row of some level among its 8 rows, or (all bits)
+            // a pivot outside the guard's span.  colmask: the levels whose pivot COLUMN lies in this strip — the warp
+            // then runs the lazy levels and overwrites that one column after each (:160)
+            uint32_t slow = guarded_all, colmask = 0;
+            if (touch) {
+                for (int l = 0; l < f; ++l) {
+                    const int cl = W.lvl[l].c, rl = W.lvl[l].r - i0;
+                    if (cl >= j0 && cl < j0 + LZ_SC) colmask |= 1u << l;
+                    if (rl >= 0 && rl < rows) slow |= 1u << (rl >> 3);
                 }
             }
-            if (__builtin_expect(!ok, 0)) {
-                // a quotient left the fast path's exponent range: redo the batch from the stored cells
+            for (int left = full; left > 0; left -= FUP_UNROLL, slow >>= 1) {
+                if (pf_ok && left >= 2 * FUP_UNROLL) asm volatile("prefetch.global.L2 [%0];" :: "l"(sp + pfo));
+                const double *cols = s_cols + (full - left);
+                bool redo = (slow & 1u) != 0;
+                if (!redo) {
+                    if (colmask) {
+                        const int jj = j0 + 2 * lane;
+                        for (int l = 0; l < f; ++l) {
+                            lazy_level(t, my_rows[l * (LZ_SC / 2)], W.py[l], cols + l * tr);
+                            const int cl = W.lvl[l].c;
+                            if (((colmask >> l) & 1u) && (cl == jj || cl == jj + 1)) {   // one lane of the warp
+                                const PivotDiv d = W.lvl[l].d;
+#pragma unroll
+                                for (int u = 0; u < FUP_UNROLL; ++u) {
+                                    const double qv = pivot_div(cols[l * tr + u], d);    // :159-160
+                                    if (cl == jj) t[u].x = qv; else t[u].y = qv;
+                                }
+                            }
+                        }
+                    } else if (f == FUSE_MAX) {
+#pragma unroll
+                        for (int l = 0; l < FUSE_MAX; ++l) lazy_level(t, my_rows[l * (LZ_SC / 2)], W.py[l], cols + l * tr);
+                    } else {
+                        for (int l = 0; l < f; ++l) lazy_level(t, my_rows[l * (LZ_SC / 2)], W.py[l], cols + l * tr);
+                    }
+                    float lo = __uint_as_float(0x7f000000u), hi = 0.0f;
+#pragma unroll
+                    for (int u = 0; u < FUP_UNROLL; ++u) range_fold(lo, hi, t[u].x, t[u].y);
+                    redo = !range_ok(lo, hi);
+                    if (__builtin_expect(redo, 0)) {
+#pragma unroll
+                        for (int u = 0; u < FUP_UNROLL; ++u)
+                            t[u] = ld_stream(reinterpret_cast<const double *>(sp + (uint64_t)ldb * u));
+                    }
+                }
+                if (__builtin_expect(redo, 0)) {
+                    const int row0 = i0 + (full - left), jj = j0 + 2 * lane;
+#pragma unroll
+                    for (int u = 0; u < FUP_UNROLL; ++u)
+                        t[u] = guarded_pair(t[u], f, W.lvl, s_rows, lane, cols + u, tr, row0 + u, jj);
+                }
+                char *dp = const_cast<char *>(sp) + delta;
+#pragma unroll
+                for (int u = 0; u < FUP_UNROLL; ++u) st_stream(reinterpret_cast<double *>(dp + (uint64_t)ldb * u), t[u]);
+                sp += (uint64_t)ldb * FUP_UNROLL;
+                if (left > FUP_UNROLL) {
+#pragma unroll
+                    for (int u = 0; u < FUP_UNROLL; ++u)
+                        t[u] = ld_stream(reinterpret_cast<const double *>(sp + (uint64_t)ldb * u));
+                }
+            }
+            if (full < rows) {
+                // the ragged last batch of the table (n + 1 is rarely a multiple of 8): guarded road, predicated rows
+                const int left = rows - full;
+                const int jj = j0 + 2 * lane;
 #pragma unroll
                 for (int u = 0; u < FUP_UNROLL; ++u)
-                    t[u] = (ii + u < rows) ? ld_stream(srcp + (int64_t)(ii + u) * ld) : make_double2(1.0, 1.0);
-                for (int l = 0; l < f; ++l) {
-                    const double2 rj = *reinterpret_cast<const double2 *>(&s_rows[l][2 * tid]);
-                    const PivotDiv d = s_lvl[l].d;
-                    double cv[FUP_UNROLL];                               // tr and ii are multiples of 8: 64-byte aligned
-                load_cols8(cv, s_cols + (int64_t)l * tr + ii);
+                    t[u] = u < left ? ld_stream(reinterpret_cast<const double *>(sp + (uint64_t)ldb * u)) : make_double2(1.0, 1.0);
 #pragma unroll
-                    for (int u = 0; u < FUP_UNROLL; ++u) {
-                        const double ci = cv[u];
-                        t[u].x = cell_update(t[u].x, d, rj.x, ci);
-                        t[u].y = cell_update(t[u].y, d, rj.y, ci);
-                    }
-                }
-            }
-        } else {
-            for (int l = 0; l < f; ++l) {
-                const double2 rj = *reinterpret_cast<const double2 *>(&s_rows[l][2 * tid]);
-                const LevelDiv L = s_lvl[l];
-                double cv[FUP_UNROLL];                               // tr and ii are multiples of 8: 64-byte aligned
-                load_cols8(cv, s_cols + (int64_t)l * tr + ii);
+                for (int u = 0; u < FUP_UNROLL; ++u)
+                    if (u < left) t[u] = guarded_pair(t[u], f, W.lvl, s_rows, lane, s_cols + full + u, tr, i0 + full + u, jj);
+                char *dp = const_cast<char *>(sp) + delta;
 #pragma unroll
-                for (int u = 0; u < FUP_UNROLL; ++u) {
-                    const int ti = i0 + ii + u;
-                    const double ci = cv[u];
-                    t[u].x = apply_level(t[u].x, ti, j, L, rj.x, ci);
-                    t[u].y = apply_level(t[u].y, ti, j + 1, L, rj.y, ci);
-                }
+                for (int u = 0; u < FUP_UNROLL; ++u)
+                    if (u < left) st_stream(reinterpret_cast<double *>(dp + (uint64_t)ldb * u), t[u]);
             }
         }
-#pragma unroll
-        for (int u = 0; u < FUP_UNROLL; ++u)
-            if (ii + u < rows) st_stream(dstp + (int64_t)(ii + u) * ld, t[u]);
-        if (PREFETCH) {
-#pragma unroll
-            for (int u = 0; u < FUP_UNROLL; ++u) t[u] = tn[u];
-        } else if (ii + FUP_UNROLL < rows) {
-#pragma unroll
-            for (int u = 0; u < FUP_UNROLL; ++u)
-                t[u] = (ii + FUP_UNROLL + u < rows) ? ld_stream(srcp + (int64_t)(ii + FUP_UNROLL + u) * ld)
-                                                     : make_double2(1.0, 1.0);
+        if (++strip == nstrips) { strip = 0; ++rt; }
+    }
+}
+
+// adversarial self-test of the lazy guard: chain k of `count` starts from cell t[k] and goes through F levels
+// (p[l], ROW value rj[k][l], COL value ci[k][l]); out_lazy = the kernel's policy (raw chain, range test on the
+// output, guarded redo when it fails), out_ref = the guarded chain.  The host compares bits.
+__global__ void lazy_guard_selftest_kernel(const double *__restrict__ t0, const double *__restrict__ p,
+                                           const double *__restrict__ rj, const double *__restrict__ ci, int F,
+                                           int64_t count, double *__restrict__ out_lazy, double *__restrict__ out_ref,
+                                           unsigned long long *__restrict__ n_redo) {
+    __shared__ PivotDiv s_d[FUSE_MAX];
+    __shared__ int s_guarded;
+    if (threadIdx.x == 0) s_guarded = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < F) {
+        const PivotDiv d = pivot_div_prepare(p[threadIdx.x]);
+        s_d[threadIdx.x] = d;
+        const int ep = (__double2hiint(d.p) >> 20) & 0x7ff;
+        if (!d.ok || ep < 1023 - LZ_P_SPAN || ep > 1023 + LZ_P_SPAN) s_guarded = 1;
+    }
+    __syncthreads();
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < count; k += (int64_t)gridDim.x * blockDim.x) {
+        double ref = t0[k], lz = t0[k];
+        for (int l = 0; l < F; ++l) ref = cell_update(ref, s_d[l], rj[k * F + l], ci[k * F + l]);
+        bool redo = s_guarded != 0;
+        if (!redo) {
+            for (int l = 0; l < F; ++l) lz = cell_update_raw(lz, s_d[l].p, s_d[l].y, rj[k * F + l], ci[k * F + l]);
+            float lo = __uint_as_float(0x7f000000u), hi = 0.0f;
+            range_fold(lo, hi, lz, lz);
+            redo = !range_ok(lo, hi);
         }
+        if (redo) {
+            atomicAdd(n_redo, 1ull);
+            lz = t0[k];
+            for (int l = 0; l < F; ++l) lz = cell_update(lz, s_d[l], rj[k * F + l], ci[k * F + l]);
+        }
+        out_lazy[k] = lz;
+        out_ref[k] = ref;
     }
 }
 
@@ -1076,42 +1234,50 @@ int64_t fused_workspace_bytes(int n, int64_t ld) { return carve_work(nullptr, n,
 
 int64_t get_option(int key);
 
-// SPX_OPT_FUSE_VARIANT != 0: the experimental update kernel (bit 0: register prefetch of the next batch, bit 2:
-// two-instruction guard);
-// SPX_OPT_FUSE_TILE_ROWS: its tile height (0 = 64).  Returns cudaErrorNotSupported when the default kernel is selected.
+// The fused update launch.  SPX_OPT_FUSE_VARIANT 0 (default): update_lazy_kernel; 1: round 1's update_fused_kernel
+// (returns cudaErrorNotSupported here and the caller launches it).  SPX_OPT_FUSE_TILE_ROWS: tile height of the lazy
+// kernel (0 = 32; a multiple of 8 <= 256); minb: resident CTAs per SM its register budget targets (0 = 3).
 static cudaError_t launch_update_variant(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R,
                                          const PlanHeader *plan, const double *ROWS, const double *COLS, int minb,
-                                         cudaStream_t stream) {
-    const int variant = (int)get_option(SPX_OPT_FUSE_VARIANT);
-    if (variant == 0) return cudaErrorNotSupported;
+                                         bool persistent, cudaStream_t stream) {
+    if ((int)get_option(SPX_OPT_FUSE_VARIANT) == 1) return cudaErrorNotSupported;
     int tr = (int)get_option(SPX_OPT_FUSE_TILE_ROWS);
-    if (tr <= 0) tr = 64;
-    const bool prefetch = (variant & 1) != 0, guard2 = (variant & 4) != 0;
-    const size_t smem = sizeof(double) * FUSE_MAX * (FUP_TC + (size_t)tr);
-    static bool configured = false;
-    cudaError_t e;
-    if (!configured) {
-        const int cap = (int)(sizeof(double) * FUSE_MAX * (FUP_TC + 256));
-#define SPX_CFG2(MB, PF, G2) \
-        if ((e = cudaFuncSetAttribute(update_fused2_kernel<MB, PF, G2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
-#define SPX_CFG2_ALL(PF, G2) SPX_CFG2(2, PF, G2) SPX_CFG2(3, PF, G2) SPX_CFG2(4, PF, G2)
-        SPX_CFG2_ALL(false, false) SPX_CFG2_ALL(true, false) SPX_CFG2_ALL(false, true) SPX_CFG2_ALL(true, true)
-#undef SPX_CFG2_ALL
-#undef SPX_CFG2
-        configured = true;
+    if (tr <= 0) tr = 32;
+    if (minb <= 0) minb = 3;
+    int items = (int)get_option(SPX_OPT_FUSE_ITEMS);
+    if (items <= 0) items = 8;
+    const size_t smem = (FUP_THREADS / 32) * sizeof(double) * FUSE_MAX * (LZ_SC + (size_t)tr);      // per warp: rows[F][64] | cols[F][tr]
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!configured[dev]) {
+        const int cap = (int)((FUP_THREADS / 32) * sizeof(double) * FUSE_MAX * (LZ_SC + 256));
+        if ((e = cudaFuncSetAttribute(update_lazy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(update_lazy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(update_lazy_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
+        configured[dev] = true;
     }
-    dim3 grid((unsigned)((m + FUP_TC - 1) / FUP_TC), (unsigned)((n + 1 + tr - 1) / tr));
-    if (grid.x == 0) return cudaSuccess;
-#define SPX_RUN2(MB, PF, G2) \
-    update_fused2_kernel<MB, PF, G2><<<grid, FUP_THREADS, smem, stream>>>(A0, A1, n, m, ld, cbd, col0, R, tr, plan, ROWS, COLS)
-#define SPX_RUN2_MB(PF, G2) \
-    do { if (minb == 2) SPX_RUN2(2, PF, G2); else if (minb == 3) SPX_RUN2(3, PF, G2); else SPX_RUN2(4, PF, G2); } while (0)
-    if (prefetch && guard2) SPX_RUN2_MB(true, true);
-    else if (prefetch) SPX_RUN2_MB(true, false);
-    else if (guard2) SPX_RUN2_MB(false, true);
-    else SPX_RUN2_MB(false, false);
-#undef SPX_RUN2_MB
-#undef SPX_RUN2
+    const int64_t nitems = (int64_t)((m + LZ_SC - 1) / LZ_SC) * ((n + 1 + tr - 1) / tr);
+    if (m <= 0 || nitems == 0) return cudaSuccess;          // a shard without columns only prices
+    if (nitems + 64 * (FUP_THREADS / 32) >= (int64_t)1 << 31) return cudaErrorInvalidValue;
+    (void)persistent;
+    const int64_t per_cta = (int64_t)(FUP_THREADS / 32) * items;
+    const unsigned grid = (unsigned)((nitems + per_cta - 1) / per_cta);
+    if (minb == 2)
+        update_lazy_kernel<2><<<grid, FUP_THREADS, smem, stream>>>(A0, A1, n, m, ld, cbd, col0, R, tr, items, plan, ROWS, COLS);
+    else if (minb == 4)
+        update_lazy_kernel<4><<<grid, FUP_THREADS, smem, stream>>>(A0, A1, n, m, ld, cbd, col0, R, tr, items, plan, ROWS, COLS);
+    else
+        update_lazy_kernel<3><<<grid, FUP_THREADS, smem, stream>>>(A0, A1, n, m, ld, cbd, col0, R, tr, items, plan, ROWS, COLS);
+    spx_host::count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t lazy_guard_selftest(const double *t0, const double *p, const double *rj, const double *ci, int F, int64_t count,
+                                double *out_lazy, double *out_ref, unsigned long long *n_redo, cudaStream_t stream) {
+    lazy_guard_selftest_kernel<<<592, 256, 0, stream>>>(t0, p, rj, ci, F, count, out_lazy, out_ref, n_redo);
     spx_host::count_launch();
     return cudaGetLastError();
 }
@@ -1165,7 +1331,7 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
     if (e != cudaSuccess) return e;
     if (phase != 2) spx_host::count_launch();
     if (phase == 1) return cudaSuccess;
-    if ((e = launch_update_variant(A0, A1, n, m, ld, cbd, col0, 1, plan, ROWS, COLS, minb, stream)) != cudaErrorNotSupported)
+    if ((e = launch_update_variant(A0, A1, n, m, ld, cbd, col0, 1, plan, ROWS, COLS, minb, true, stream)) != cudaErrorNotSupported)
         return e;
     static bool configured = false;
     if (!configured) {
@@ -1251,7 +1417,8 @@ static cudaError_t launch_shard_price(const FusedCtx &c, const FusedWork &w, int
     return e;
 }
 
-static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, int h, int minb, cudaStream_t stream) {
+static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, int h, int minb, bool persistent,
+                                       cudaStream_t stream) {
     const int slot3 = (int)(c.seq % 3ull);               // the COL planes of this pass (c.seq = its pass number)
     static bool configured = false;
     cudaError_t e;
@@ -1265,7 +1432,7 @@ static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, in
     const double *COLS = reinterpret_cast<const double *>(static_cast<unsigned char *>(c.xbox[c.rank]) + XL.cols_off) +
                          (int64_t)slot3 * FUSE_MAX * c.R * cbd;
     if ((e = launch_update_variant(c.A[0], c.A[1], c.n, c.m_loc, c.ld, cbd, c.col0, c.R, w.plan[h], w.ROWS[h], COLS, minb,
-                                   stream)) != cudaErrorNotSupported)
+                                   persistent, stream)) != cudaErrorNotSupported)
         return e;
     dim3 grid((unsigned)((c.m_loc + FUP_TC - 1) / FUP_TC), (unsigned)((c.n + 1 + FUP_TR - 1) / FUP_TR));
     if (grid.x == 0) return cudaSuccess;                     // a shard without columns only prices
@@ -1303,11 +1470,11 @@ cudaError_t fused_run(FusedCtx &c, int64_t pivots, int depth, int minb, bool loo
             if ((e = launch_shard_price(c, w, F, h, q > 0, c.side)) != cudaSuccess) return e;
             if ((e = cudaEventRecord(c.ev_priced[h], c.side)) != cudaSuccess) return e;
             if ((e = cudaStreamWaitEvent(s, c.ev_priced[h], 0)) != cudaSuccess) return e;
-            if ((e = launch_fused_update(c, w, h, minb, s)) != cudaSuccess) return e;
+            if ((e = launch_fused_update(c, w, h, minb, false, s)) != cudaSuccess) return e;
             if ((e = cudaEventRecord(c.ev_upd[h], s)) != cudaSuccess) return e;
         } else {
             if ((e = launch_shard_price(c, w, F, h, false, s)) != cudaSuccess) return e;
-            if ((e = launch_fused_update(c, w, h, minb, s)) != cudaSuccess) return e;
+            if ((e = launch_fused_update(c, w, h, minb, true, s)) != cudaSuccess) return e;
         }
         left -= F;
     }

@@ -30,7 +30,7 @@ class loop_mode:
             assert N.lib().spx_set_option(8, 2) == 0
             return "fused"
         if isinstance(self.name, str) and self.name.startswith("fused-x"):   # "fused-x<variant>-<tile rows>[-<minb>]":
-            parts = self.name[len("fused-x"):].split("-")                    # the experimental update kernel
+            parts = self.name[len("fused-x"):].split("-")                    # update kernel schedule
             assert N.lib().spx_set_option(10, int(parts[0])) == 0
             assert N.lib().spx_set_option(11, int(parts[1])) == 0
             assert N.lib().spx_set_option(7, int(parts[2]) if len(parts) > 2 else 0) == 0
@@ -707,19 +707,17 @@ def test_column_sharded_ranks_emulated_entering_column_on_late_ranks(spx, world,
     _emulated_ranks(spx, world, n, m, rows, c, cap, lookahead, exchange)
 
 
-# --------------------------------------------------------------------------- experimental fused update kernel
-EXPERIMENTAL = __import__("os").environ.get("SPX_EXPERIMENTAL", "0") == "1"
-X_MODES = ["fused-x2-32", "fused-x6-64", "fused-x2-256", "fused-x3-64-2", "fused-x7-128-2", "fused-x7-40-3", "fused-x3-8",
-           "fused-x6-32-4"]
+# --------------------------------------------------------------------------- fused update kernel schedules
+# "fused-x<variant>-<tile rows>[-<min blocks>]": variant 0 = update_lazy_kernel (the default: ONE range test per cell
+# per pass), 1 = round 1's update_fused_kernel (a range test per cell per level)
+X_MODES = ["fused-x0-32", "fused-x0-64-2", "fused-x0-256-3", "fused-x0-8-4", "fused-x0-40-2", "fused-x1-0", "fused-x1-0-3"]
 
 
-@pytest.mark.skipif(not EXPERIMENTAL, reason="update_fused2_kernel (SPX_OPT_FUSE_VARIANT) was written after round 1's GPU "
-                    "budget was spent and has not run on hardware: set SPX_EXPERIMENTAL=1")
 @pytest.mark.parametrize("mode", X_MODES)
-def test_experimental_fused_update_variant(spx, ref_cases, cfg_digests, mode):
-    """Every schedule of the experimental fused update kernel (tile height, register prefetch, occupancy target)
-    must produce the default kernel's bits: ragged shapes in steps of 1..9 pivots, the reference's golden cases,
-    and the first 300 pivots of cfg2."""
+def test_fused_update_kernel_schedules(spx, ref_cases, cfg_digests, mode):
+    """Every schedule of the fused update (kernel, tile height, occupancy target) must produce the oracle's bits:
+    ragged shapes in steps of 1..9 pivots, the reference's golden cases (zeros, degenerate ties, phase 1 — the
+    lazy guard's re-do path), and the first 300 pivots of cfg2."""
     with loop_mode(mode) as mode_:
         for n, m in [(1, 2), (3, 1), (7, 15), (65, 513), (130, 1030), (257, 100), (300, 700), (40, 2049)]:
             _ragged_loop(spx, n, m, mode_)
@@ -737,3 +735,80 @@ def test_experimental_fused_update_variant(spx, ref_cases, cfg_digests, mode):
         dev.solve(stop_after=300, lookahead=mode_)
         assert dev.trace[:300].cpu().numpy().tolist() == o.trace.tolist()
         assert np.array_equal(bits(dev.export_flat(300)), bits(o.table))
+
+
+def test_lazy_range_guard_adversarial_chains(spx):
+    """The fused update divides WITHOUT a per-level range test and checks only the outputs of a pass
+    (csrc/spx_fused.cu, update_lazy_kernel).  Adversarial 8-level chains — exact zeros, subnormals, cancellation
+    down to 2^-1000 followed by growth, overflow, pivots at and beyond the guard's span — through the kernel's
+    policy and through the per-level guarded division: every bit must agree."""
+    import ctypes
+    torch = spx.torch
+    L = spx.N.lib()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(20261018)
+    F, cnt = 8, 1 << 20
+
+    def rnd(lo_exp, hi_exp, shape):
+        """random doubles with biased exponent in [lo_exp, hi_exp] (0 = zeros / subnormals), random sign"""
+        numel = int(np.prod(shape))
+        mant = torch.randint(0, 1 << 52, (numel,), generator=g, device="cuda", dtype=torch.int64)
+        exp = torch.randint(lo_exp, hi_exp + 1, (numel,), generator=g, device="cuda", dtype=torch.int64)
+        sign = torch.randint(0, 2, (numel,), generator=g, device="cuda", dtype=torch.int64) << 63
+        return (mant | (exp << 52) | sign).view(torch.float64).reshape(shape)
+
+    def sprinkle(x, frac, value):
+        m = torch.rand(x.shape, generator=g, device="cuda") < frac
+        return torch.where(m, torch.full_like(x, value), x)
+
+    def growth(e0, step):
+        """level l multipliers with exponent e0 + step * l (+- 3): what a tiny cell meets on its way up"""
+        base = torch.arange(F, device="cuda", dtype=torch.int64)[None, :] * step + e0
+        jit = torch.randint(-3, 4, (cnt, F), generator=g, device="cuda", dtype=torch.int64)
+        e = (base + jit).clamp(1, 2046)
+        mant = torch.randint(0, 1 << 52, (cnt, F), generator=g, device="cuda", dtype=torch.int64)
+        sign = torch.randint(0, 2, (cnt, F), generator=g, device="cuda", dtype=torch.int64) << 63
+        return (mant | (e << 52) | sign).view(torch.float64)
+
+    one = torch.ones((cnt, F), dtype=torch.float64, device="cuda")
+    pivots = [rnd(1023 - 2, 1023 + 2, (F,)), rnd(1023 - 100, 1023 + 100, (F,)),
+              torch.tensor([2.0 ** -100, -2.0 ** 100, 1.5 * 2.0 ** 100, 2.0 ** -100 * 1.999, 1.0, -3.0, 0.1, 7e29],
+                           dtype=torch.float64, device="cuda"),
+              torch.tensor([1.0, 2.0 ** -101, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0], dtype=torch.float64, device="cuda"),   # guarded
+              torch.tensor([1.0, 1.0, 2.0 ** 500, 1.0, 5e-324, 1.0, 1.0, 1.0], dtype=torch.float64, device="cuda")]  # guarded
+    suites = []
+    # ordinary magnitudes, with exact zeros sprinkled over cells, rows and columns (sparse tableaus)
+    suites.append((sprinkle(rnd(1023 - 30, 1023 + 30, (cnt,)), 0.1, 0.0), sprinkle(rnd(1023 - 30, 1023 + 30, (cnt, F)), 0.2, 0.0),
+                   sprinkle(rnd(1023 - 30, 1023 + 30, (cnt, F)), 0.2, -0.0)))
+    # whole exponent range
+    suites.append((rnd(0, 2046, (cnt,)), rnd(0, 2046, (cnt, F)), rnd(0, 2046, (cnt, F))))
+    # tiny cells (subnormal .. 2^-900) meeting multipliers that grow by 2^step per level, products rj * ci with ci = 1
+    for e0, step in [(1, 40), (10, 54), (30, 55), (60, 56), (1, 60), (1, 100), (100, 0), (1, 128)]:
+        suites.append((sprinkle(rnd(0, 123, (cnt,)), 0.05, 0.0), growth(e0, step), one))
+    # cancellation: rj * ci equals t * p to the last bits at level 0 (ci = p0), then ordinary / tiny levels
+    for lo, hi in [(1023 - 20, 1023 + 20), (1, 200)]:
+        t0 = rnd(1023 - 940, 1023 - 900, (cnt,)) if lo == 1 else rnd(1023 - 20, 1023 + 20, (cnt,))
+        rj = rnd(lo, hi, (cnt, F))
+        rj[:, 0] = t0 * (1.0 + (torch.randint(-2, 3, (cnt,), generator=g, device="cuda").double() * 2.0 ** -52))
+        suites.append((t0, rj, None))                      # ci[:, 0] = p[0] is filled in per pivot set
+    # overflow on the way
+    suites.append((rnd(2000, 2046, (cnt,)), rnd(1023 - 5, 1023 + 600, (cnt, F)), rnd(1023 - 5, 1023 + 400, (cnt, F))))
+    redo_total = 0
+    for p in pivots:
+        p = p.contiguous()
+        for t0, rj, ci in suites:
+            if ci is None:
+                ci = rnd(1023 - 20, 1023 + 20, (cnt, F))
+                ci[:, 0] = p[0]
+            t0 = t0.contiguous(); rj = rj.contiguous(); ci = ci.contiguous()
+            lz, ref = torch.empty_like(t0), torch.empty_like(t0)
+            redo = ctypes.c_uint64(0)
+            rc = L.spx_selftest_lazy_guard(t0.data_ptr(), p.data_ptr(), rj.data_ptr(), ci.data_ptr(), F, cnt,
+                                           lz.data_ptr(), ref.data_ptr(), ctypes.byref(redo),
+                                           torch.cuda.current_stream().cuda_stream)
+            assert rc == 0
+            bad = (lz.view(torch.int64) != ref.view(torch.int64)).nonzero()
+            assert bad.numel() == 0, (int(bad.numel()), int(bad[0]), float(t0[bad[0]]).hex(),
+                                      float(lz[bad[0]]).hex(), float(ref[bad[0]]).hex())
+            redo_total += redo.value
+    assert redo_total > 0                                   # the suites do reach the re-do path
