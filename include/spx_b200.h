@@ -102,8 +102,8 @@ int64_t     spx_launch_count(int reset);
 #define SPX_OPT_FUSE_PRICING     8  /* fused loop pricing kernel: 0 auto, 1 one CTA, 2 whole-GPU cooperative */
 #define SPX_OPT_FUSE_LOOKAHEAD   9  /* fused loop in spx_solve: 1 = price pass q+1 on a side stream during update q (default 0: off on one GPU) */
 #define SPX_OPT_FUSE_VARIANT     10 /* fused update kernel: 0 default (lazy range guard: one range test per cell per PASS), 1 = round 1's kernel (range test per cell per level) */
-#define SPX_OPT_FUSE_TILE_ROWS   11 /* fused update kernel: rows per item (0 = 32; a multiple of 8 <= 256) */
-#define SPX_OPT_FUSE_ITEMS       12 /* fused update kernel: 64-column x TILE_ROWS items per warp (0 = 8; 1..64) */
+#define SPX_OPT_FUSE_TILE_ROWS   11 /* fused update kernel: rows of the strip one warp walks (0 = 128; a multiple of 8 <= 4096) */
+#define SPX_OPT_FUSE_PAIRS       12 /* fused update kernel: column pairs per lane, i.e. strip width / 64 (0 = default 2; 1 or 2) */
 int         spx_set_option(int32_t option, int64_t value);
 int64_t     spx_get_option(int32_t option);
 /* Device self-test of the hoisted-reciprocal division used by K3 against the

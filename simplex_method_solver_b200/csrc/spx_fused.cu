@@ -927,223 +927,257 @@ __device__ __forceinline__ void lazy_level(double2 (&t)[FUP_UNROLL], const doubl
 // formulas with the fully guarded division (pivot row :156, pivot column :160, pivot cell :163, ordinary cells
 // :173-175), one row pair per call.  Not inlined and by value: neither its registers nor an addressable copy of the
 // batch may weigh on the steady state.
-__device__ __noinline__ double2 guarded_pair(double2 t, int f, const LevelDiv *s_lvl, const double *s_rows, int lane,
-                                             const double *col, int tr, int row, int j) {
+__device__ __noinline__ double2 guarded_pair(double2 t, int f, const LevelDiv *s_lvl, const double2 *my_rows, int rstride,
+                                             const double *col, int cstride, int row, int j) {
     for (int l = 0; l < f; ++l) {
-        const double2 rj = *reinterpret_cast<const double2 *>(s_rows + l * 64 + 2 * lane);
+        const double2 rj = my_rows[l * rstride];
         const LevelDiv L = s_lvl[l];
-        const double ci = col[l * tr];
+        const double ci = col[l * cstride];
         t.x = apply_level(t.x, row, j, L, rj.x, ci);
         t.y = apply_level(t.y, row, j + 1, L, rj.y, ci);
     }
     return t;
 }
 
-// WARP-AUTONOMOUS: there is no CTA-wide barrier, no mbarrier and no elected producer in this kernel.  An item is a
-// 64-column strip x tr rows; warp w of CTA b owns the `items` consecutive items (b * 8 + w) * items ... (adjacent
-// strips of the same row tile, so a CTA covers 8 * items * 64 contiguous columns).  Each warp keeps ITS OWN slices
-// in shared memory: every lane loads the 8 ROW_l values of ITS two columns with 128-bit loads and parks them in
-// its own shared-memory slot (nobody else reads them: no synchronisation), and the 8 x tr COL_l multipliers of the
-// row tile are copied cooperatively when the row tile changes (one __syncwarp).  These loads are issued together
-// with the first 8 rows of the item, so their latency hides behind the global loads the warp waits for anyway.
-// Why not CTA-wide TMA staging as in K3 / round 1's kernel: measured (profiles/r2/), (i) with CTA-wide staging the
-// warps of all co-resident CTAs moved in lock step — prologue barrier + TMA round trip together, hot loops
-// together — and the fp64 pipe idled ~25 % of the time although 2.6 warps per scheduler were ready on average;
-// (ii) the dispatch port is the binding resource: an fp64 warp instruction holds it for 2 cycles, any other for 1
+// WARP-AUTONOMOUS STRIP WALKER.  A warp owns a 64-column strip x `rw` rows (rw a multiple of 8) and walks down it
+// in batches of 8 rows; after one barrier at kernel start (the levels' divisors, shared by the CTA) warps never
+// synchronise with each other again.  Everything a batch needs arrives ASYNCHRONOUSLY while the previous batch
+// computes (cp.async, 16 bytes per lane per row):
+//   * the cells: lane L copies ITS pair of columns of the next 8 rows into its own 8 shared-memory slots (nobody
+//     else reads them), and moves them to registers with eight 128-bit shared loads when the batch starts;
+//   * the 8 levels x 8 rows of COL multipliers of the next batch (512 bytes: one 16-byte copy per lane) into a
+//     double-buffered warp-wide slot (one __syncwarp per batch makes them visible);
+//   * the 8 ROW values of a lane's two columns are loaded once per strip into the lane's own slots.
+// So no warp ever waits for HBM in the steady state, with 2-3 warps per scheduler.  How the design got here
+// (profiles/r2/): (i) round 1's per-level range guard was 20 % of the dispatch slots — gone (lazy guard above);
+// (ii) CTA-wide TMA staging made the warps of all co-resident CTAs move in lock step (prologue barrier + TMA round
+// trip together, hot loops together): the fp64 pipe idled ~25 % of the time although 2.6 warps per scheduler were
+// ready on average; a persistent CTA variant with double-buffered TMA stages still paid a barrier per tile and a
+// static tail; (iii) warp-private slices without prefetch left ~16 % of the warp time in long-scoreboard waits.
+// The dispatch port is the binding resource: an fp64 warp instruction holds it for 2 cycles, any other for 1
 // (tools/fp64_lab.cu reproduces every measured pipe utilisation with that model), so every instruction that is not
-// one of the 6 fp64 issues per cell-level costs fp64 throughput — the elected-lane cp.async.bulk loops (16 copies
-// per item) and the mbarrier polling were ~1/3 of the non-fp64 instructions.
-constexpr int LZ_SC = 64;                       // columns per strip (2 per lane)
-
-struct LazyWarpSmem {                           // static shared memory of one warp
-    LevelDiv lvl[FUSE_MAX];
-    double2  py[FUSE_MAX];                      // (p, y) per level: one 128-bit load
-    int      guarded;                           // some pivot of the pass is outside the lazy guard's span
-    int      pad[3];
+// one of the 6 fp64 issues per cell-level costs fp64 throughput.
+// NP = column PAIRS per lane: a warp's strip is 64 * NP columns (lane L owns columns 2L, 2L + 1 of each 64-column
+// half).  NP = 2 halves the per-cell cost of everything that is per batch or per level (multiplier loads, address
+// arithmetic, the loop) at the price of 2 x the registers and shared memory per warp (12 warps per SM).
+template <int NP> struct LazyGeom {
+    static constexpr int SC = 64 * NP;                          // columns per strip
+    static constexpr int T_BYTES = 8 * NP * 32 * 16;            // cells of one batch: [8 rows][NP][32 lanes] double2
+    static constexpr int R_BYTES = FUSE_MAX * NP * 32 * 16;     // ROW values: [FUSE_MAX][NP][32 lanes] double2
+    static constexpr int C_BYTES = 2 * FUSE_MAX * 8 * 8;        // COL multipliers: [2][FUSE_MAX][8 rows]
+    static constexpr int WARP_BYTES = T_BYTES + R_BYTES + C_BYTES;
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(FUP_THREADS, MINB)
-update_lazy_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R, int tr, int items,
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// one level on a lane's 8 x NP pairs, no guard
+template <int NP>
+__device__ __forceinline__ void lazy_level_np(double2 (&t)[FUP_UNROLL][NP], const double2 *rows_l, const double2 py,
+                                              const double *cols) {
+    double cv[FUP_UNROLL];
+    load_cols8(cv, cols);
+    double2 rj[NP];
+#pragma unroll
+    for (int h = 0; h < NP; ++h) rj[h] = rows_l[h * 32];
+#pragma unroll
+    for (int u = 0; u < FUP_UNROLL; ++u) {
+#pragma unroll
+        for (int h = 0; h < NP; ++h) {
+            t[u][h].x = cell_update_raw(t[u][h].x, py.x, py.y, rj[h].x, cv[u]);
+            t[u][h].y = cell_update_raw(t[u][h].y, py.x, py.y, rj[h].y, cv[u]);
+        }
+    }
+}
+
+template <int NP, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+update_lazy_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R, int rw,
                    const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
                    const double *__restrict__ COLS) {
+    using G = LazyGeom<NP>;
     const int f = plan->f;
     if (f <= 0) return;
     extern __shared__ __align__(128) unsigned char lz_raw[];
-    __shared__ __align__(16) LazyWarpSmem s_w[FUP_THREADS / 32];
+    __shared__ LevelDiv s_lvl[FUSE_MAX];
+    __shared__ __align__(16) double2 s_py[FUSE_MAX];             // (p, y) per level: one 128-bit load
+    __shared__ const double *s_colp[FUSE_MAX];                   // COL_l plane of each level
+    __shared__ int s_guarded;                                    // some pivot of the pass is outside the lazy guard's span
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    LazyWarpSmem &W = s_w[warp];
-    double *s_rows = reinterpret_cast<double *>(lz_raw + (size_t)warp * sizeof(double) * FUSE_MAX * (LZ_SC + tr));   // [FUSE_MAX][64]
-    double *s_cols = s_rows + FUSE_MAX * LZ_SC;                                                                     // [FUSE_MAX][tr]
+    unsigned char *wbase = lz_raw + (size_t)warp * G::WARP_BYTES;
+    double2 *my_t = reinterpret_cast<double2 *>(wbase) + lane;                            // row u, half h: my_t[(u * NP + h) * 32]
+    double2 *my_rows = reinterpret_cast<double2 *>(wbase + G::T_BYTES) + lane;            // level l, half h: my_rows[(l * NP + h) * 32]
+    double *s_colbuf = reinterpret_cast<double *>(wbase + G::T_BYTES + G::R_BYTES);       // [2][FUSE_MAX][8]
 
     const int src = plan->src;
     const double *__restrict__ Ain = src ? A1 : A0;
     double *__restrict__ Aout = src ? A0 : A1;
 
-    const int nstrips = (m + LZ_SC - 1) / LZ_SC;
-    const int nrt = (n + 1 + tr - 1) / tr;
-    const int nitems = nstrips * nrt;                           // < 2^31: checked by the launcher
-    const int first = (blockIdx.x * (FUP_THREADS / 32) + warp) * items;
-    if (first >= nitems) return;
-    const int last = min(first + items, nitems) - 1;
-
-    // ---- once per warp: the levels (the same for every item); does any pivot row / column touch this warp's items?
-    if (lane == 0) W.guarded = 0;
-    __syncwarp();
-    bool touch = false;
-    if (lane < f) {
-        const double p = plan->lvl[lane].p;
-        const int rl = plan->lvl[lane].r;
-        W.lvl[lane].r = rl;
-        const int64_t cg = (int64_t)plan->lvl[lane].c - col0;       // the plan carries GLOBAL column indices
-        const int cl = (cg >= 0 && cg < m) ? (int)cg : -1;
-        W.lvl[lane].c = cl;
+    // ---- once per CTA: the levels
+    if (threadIdx.x == 0) s_guarded = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < f) {
+        const int l = threadIdx.x;
+        const double p = plan->lvl[l].p;
+        s_lvl[l].r = plan->lvl[l].r;
+        const int64_t cg = (int64_t)plan->lvl[l].c - col0;           // the plan carries GLOBAL column indices
+        s_lvl[l].c = (cg >= 0 && cg < m) ? (int)cg : -1;
         const PivotDiv d = pivot_div_prepare(p);
-        W.lvl[lane].d = d;
-        W.py[lane] = make_double2(d.p, d.y);
+        s_lvl[l].d = d;
+        s_py[l] = make_double2(d.p, d.y);
+        s_colp[l] = COLS + ((int64_t)l * R + plan->owner[l]) * cbd;
         const int ep = (__double2hiint(p) >> 20) & 0x7ff;
-        if (!d.ok || ep < 1023 - LZ_P_SPAN || ep > 1023 + LZ_P_SPAN) W.guarded = 1;
-        // items first..last cover row tiles first / nstrips .. last / nstrips; a pivot row in one of them, or (one row
-        // tile only) a pivot column in one of the strips, or (several row tiles) any local pivot column
-        const int rt0 = first / nstrips, rt1 = last / nstrips;
-        const int prt = rl / tr;
-        touch = prt >= rt0 && prt <= rt1;
-        if (cl >= 0) {
-            const int ps = cl / LZ_SC;
-            touch = touch || rt1 > rt0 || (ps >= first - rt0 * nstrips && ps <= last - rt0 * nstrips);
-        }
+        if (!d.ok || ep < 1023 - LZ_P_SPAN || ep > 1023 + LZ_P_SPAN) s_guarded = 1;
     }
-    touch = __any_sync(0xffffffffu, touch);
-    __syncwarp();
+    __syncthreads();
+
+    const int nstrips = (m + G::SC - 1) / G::SC;
+    const int nchunks = (n + 1 + rw - 1) / rw;
+    const int w = blockIdx.x * (THREADS / 32) + warp;           // < 2^31: checked by the launcher
+    if (w >= nstrips * nchunks) return;
+    const int chunk = w / nstrips, strip = w - chunk * nstrips;
+    const int j0 = strip * G::SC, i0 = chunk * rw;
+    const int jj = j0 + 2 * lane;                                // half h: columns jj + 64 h, jj + 64 h + 1
+    const int rows = min(rw, n + 1 - i0);
+    const int nb = rows >> 3;                                    // whole batches
+    bool active[NP];
+#pragma unroll
+    for (int h = 0; h < NP; ++h) active[h] = jj + 64 * h < m;
 
     // row pitch in bytes fits 32 bits (ld <= 2^28 doubles): every row address is ONE IMAD.WIDE.U32 off the batch base
     const uint32_t ldb = (uint32_t)(ld * 8);
     const int64_t delta = reinterpret_cast<const char *>(Aout) - reinterpret_cast<const char *>(Ain);
-    // L2 prefetch of the batch after the one in registers: lane L touches 128-byte line (L & 3) of row (L >> 2);
-    // the per-lane offset from this thread's batch base fits 32 bits for ld < 2^24 doubles (else: no prefetch)
-    const uint32_t pfo = ldb * (uint32_t)(FUP_UNROLL + (lane >> 2)) + 128u * (lane & 3) - 16u * lane;
-    const bool pf_ok = ld < (1 << 24);
-    const uint32_t guarded_all = W.guarded ? 0xffffffffu : 0u;
-    double2 *my_rows = reinterpret_cast<double2 *>(s_rows) + lane;                       // level l: my_rows[l * 32]
+    const char *sp = reinterpret_cast<const char *>(Ain + (int64_t)i0 * ld + jj);         // this lane's first pair, first row of the batch
+    // this lane's share of a batch's COL multipliers: 16 bytes = rows 2k, 2k + 1 of level l, lane = 4 l + k
+    const double *my_colsrc = (lane < 4 * f) ? s_colp[lane >> 2] + i0 + 2 * (lane & 3) : nullptr;
+    double *my_coldst = s_colbuf + (lane >> 2) * 8 + 2 * (lane & 3);
 
-    int rt = first / nstrips, strip = first - rt * nstrips, rt_staged = -1;
-    for (int it = first; it <= last; ++it) {
-        const int j0 = strip * LZ_SC, i0 = rt * tr;
-        const int rows = min(tr, n + 1 - i0);
-        const int full = rows & ~(FUP_UNROLL - 1);                                        // rows in whole batches
-        const bool active = j0 + 2 * lane < m;
-        const char *sp = reinterpret_cast<const char *>(Ain + (int64_t)i0 * ld + j0 + 2 * lane);  // this lane's pair, first row
-        double2 t[FUP_UNROLL];
-        // the first batch, this lane's 8 ROW values and (new row tile) the COL multipliers: all in flight together
-        if (active && full > 0) {
+    auto fetch_batch = [&](const char *from, int b) {           // cells + multipliers of batch b, asynchronously
 #pragma unroll
-            for (int u = 0; u < FUP_UNROLL; ++u) t[u] = ld_stream(reinterpret_cast<const double *>(sp + (uint64_t)ldb * u));
-        }
-        if (active) {
-            const double *rp = ROWS + j0 + 2 * lane;
-            if (f == FUSE_MAX) {
+        for (int h = 0; h < NP; ++h) {
+            if (active[h]) {
 #pragma unroll
-                for (int h = 0; h < FUSE_MAX; h += 4) {
-                    double2 rv[4];
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) rv[l] = __ldg(reinterpret_cast<const double2 *>(rp + (int64_t)(h + l) * ld));
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) my_rows[(h + l) * (LZ_SC / 2)] = rv[l];
-                }
-            } else {
-                for (int l = 0; l < f; ++l) my_rows[l * (LZ_SC / 2)] = __ldg(reinterpret_cast<const double2 *>(rp + (int64_t)l * ld));
+                for (int u = 0; u < FUP_UNROLL; ++u) cp_async16(my_t + (u * NP + h) * 32, from + (uint64_t)ldb * u + 512 * h);
             }
         }
-        if (rt != rt_staged) {
-            __syncwarp();                                        // every lane is done with the previous row tile's multipliers
-            const int ncol = (int)min((int64_t)tr, cbd - i0);    // planes hold cbd >= n + 1 cells
+        if (my_colsrc) cp_async16(my_coldst + (b & 1) * (FUSE_MAX * 8), my_colsrc + 8 * b);
+        cp_async_commit();
+    };
+
+    if (nb > 0) fetch_batch(sp, 0);
+#pragma unroll
+    for (int h = 0; h < NP; ++h) {                               // this lane's ROW values, once per strip
+        if (active[h]) {
+            const double *rp = ROWS + jj + 64 * h;
+            for (int l = 0; l < f; ++l) my_rows[(l * NP + h) * 32] = __ldg(reinterpret_cast<const double2 *>(rp + (int64_t)l * ld));
+        }
+    }
+    // colmask: the levels whose pivot COLUMN lies in this strip — the warp then runs the lazy levels and overwrites
+    // that one column after each (:160); rowhit: some level's pivot ROW lies in this warp's rows (then every batch
+    // looks for it); guarded_all: a pivot outside the guard's span sends every batch down the guarded road
+    uint32_t colmask = 0;
+    bool rowhit = false;
+    for (int l = 0; l < f; ++l) {
+        const int cl = s_lvl[l].c, rl = s_lvl[l].r - i0;
+        if (cl >= j0 && cl < j0 + G::SC) colmask |= 1u << l;
+        rowhit = rowhit || (rl >= 0 && rl < rows);
+    }
+    const bool guarded_all = s_guarded != 0;
+
+    for (int b = 0; b < nb; ++b) {
+        cp_async_wait_all();
+        __syncwarp();                                            // batch b: my cells, everybody's multipliers
+        double2 t[FUP_UNROLL][NP];
+#pragma unroll
+        for (int u = 0; u < FUP_UNROLL; ++u)
+#pragma unroll
+            for (int h = 0; h < NP; ++h) t[u][h] = my_t[(u * NP + h) * 32];
+        const double *cols = s_colbuf + (b & 1) * (FUSE_MAX * 8);
+        bool redo = guarded_all;
+        if (rowhit) {
             for (int l = 0; l < f; ++l) {
-                const double *cp = COLS + ((int64_t)l * R + plan->owner[l]) * cbd + i0;
-                for (int u = lane; u < ncol; u += 32) s_cols[l * tr + u] = __ldcg(cp + u);
+                const int rl = s_lvl[l].r - i0 - 8 * b;
+                redo = redo || (rl >= 0 && rl < 8);
             }
-            __syncwarp();
-            rt_staged = rt;
         }
-        if (active) {
-            // bit b of slow: batch b takes the guarded road — a pivot row of some level among its 8 rows, or (all bits)
-            // a pivot outside the guard's span.  colmask: the levels whose pivot COLUMN lies in this strip — the warp
-            // then runs the lazy levels and overwrites that one column after each (:160)
-            uint32_t slow = guarded_all, colmask = 0;
-            if (touch) {
+        if (b + 1 < nb) fetch_batch(sp + (uint64_t)ldb * FUP_UNROLL, b + 1);
+        if (!redo) {
+            if (colmask) {
                 for (int l = 0; l < f; ++l) {
-                    const int cl = W.lvl[l].c, rl = W.lvl[l].r - i0;
-                    if (cl >= j0 && cl < j0 + LZ_SC) colmask |= 1u << l;
-                    if (rl >= 0 && rl < rows) slow |= 1u << (rl >> 3);
-                }
-            }
-            for (int left = full; left > 0; left -= FUP_UNROLL, slow >>= 1) {
-                if (pf_ok && left >= 2 * FUP_UNROLL) asm volatile("prefetch.global.L2 [%0];" :: "l"(sp + pfo));
-                const double *cols = s_cols + (full - left);
-                bool redo = (slow & 1u) != 0;
-                if (!redo) {
-                    if (colmask) {
-                        const int jj = j0 + 2 * lane;
-                        for (int l = 0; l < f; ++l) {
-                            lazy_level(t, my_rows[l * (LZ_SC / 2)], W.py[l], cols + l * tr);
-                            const int cl = W.lvl[l].c;
-                            if (((colmask >> l) & 1u) && (cl == jj || cl == jj + 1)) {   // one lane of the warp
-                                const PivotDiv d = W.lvl[l].d;
+                    lazy_level_np<NP>(t, my_rows + l * NP * 32, s_py[l], cols + l * 8);
+                    const int cl = s_lvl[l].c - jj;              // 0 / 1 (+ 64 h): this lane holds the pivot column
+                    if (((colmask >> l) & 1u) && cl >= 0 && (cl & 63) < 2 && cl < G::SC) {
+                        const PivotDiv d = s_lvl[l].d;
 #pragma unroll
-                                for (int u = 0; u < FUP_UNROLL; ++u) {
-                                    const double qv = pivot_div(cols[l * tr + u], d);    // :159-160
-                                    if (cl == jj) t[u].x = qv; else t[u].y = qv;
-                                }
+                        for (int u = 0; u < FUP_UNROLL; ++u) {
+                            const double qv = pivot_div(cols[l * 8 + u], d);             // :159-160
+#pragma unroll
+                            for (int h = 0; h < NP; ++h) {
+                                if (cl == 64 * h) t[u][h].x = qv;
+                                if (cl == 64 * h + 1) t[u][h].y = qv;
                             }
                         }
-                    } else if (f == FUSE_MAX) {
-#pragma unroll
-                        for (int l = 0; l < FUSE_MAX; ++l) lazy_level(t, my_rows[l * (LZ_SC / 2)], W.py[l], cols + l * tr);
-                    } else {
-                        for (int l = 0; l < f; ++l) lazy_level(t, my_rows[l * (LZ_SC / 2)], W.py[l], cols + l * tr);
-                    }
-                    float lo = __uint_as_float(0x7f000000u), hi = 0.0f;
-#pragma unroll
-                    for (int u = 0; u < FUP_UNROLL; ++u) range_fold(lo, hi, t[u].x, t[u].y);
-                    redo = !range_ok(lo, hi);
-                    if (__builtin_expect(redo, 0)) {
-#pragma unroll
-                        for (int u = 0; u < FUP_UNROLL; ++u)
-                            t[u] = ld_stream(reinterpret_cast<const double *>(sp + (uint64_t)ldb * u));
                     }
                 }
-                if (__builtin_expect(redo, 0)) {
-                    const int row0 = i0 + (full - left), jj = j0 + 2 * lane;
+            } else if (f == FUSE_MAX) {
 #pragma unroll
-                    for (int u = 0; u < FUP_UNROLL; ++u)
-                        t[u] = guarded_pair(t[u], f, W.lvl, s_rows, lane, cols + u, tr, row0 + u, jj);
-                }
-                char *dp = const_cast<char *>(sp) + delta;
-#pragma unroll
-                for (int u = 0; u < FUP_UNROLL; ++u) st_stream(reinterpret_cast<double *>(dp + (uint64_t)ldb * u), t[u]);
-                sp += (uint64_t)ldb * FUP_UNROLL;
-                if (left > FUP_UNROLL) {
-#pragma unroll
-                    for (int u = 0; u < FUP_UNROLL; ++u)
-                        t[u] = ld_stream(reinterpret_cast<const double *>(sp + (uint64_t)ldb * u));
-                }
+                for (int l = 0; l < FUSE_MAX; ++l) lazy_level_np<NP>(t, my_rows + l * NP * 32, s_py[l], cols + l * 8);
+            } else {
+                for (int l = 0; l < f; ++l) lazy_level_np<NP>(t, my_rows + l * NP * 32, s_py[l], cols + l * 8);
             }
-            if (full < rows) {
-                // the ragged last batch of the table (n + 1 is rarely a multiple of 8): guarded road, predicated rows
-                const int left = rows - full;
-                const int jj = j0 + 2 * lane;
+            float lo = __uint_as_float(0x7f000000u), hi = 0.0f;
+#pragma unroll
+            for (int u = 0; u < FUP_UNROLL; ++u)
+#pragma unroll
+                for (int h = 0; h < NP; ++h)
+                    if (active[h]) range_fold(lo, hi, t[u][h].x, t[u][h].y);   // a half beyond the last column holds stale data
+            redo = !range_ok(lo, hi);
+            if (__builtin_expect(redo, 0)) {
 #pragma unroll
                 for (int u = 0; u < FUP_UNROLL; ++u)
-                    t[u] = u < left ? ld_stream(reinterpret_cast<const double *>(sp + (uint64_t)ldb * u)) : make_double2(1.0, 1.0);
 #pragma unroll
-                for (int u = 0; u < FUP_UNROLL; ++u)
-                    if (u < left) t[u] = guarded_pair(t[u], f, W.lvl, s_rows, lane, s_cols + full + u, tr, i0 + full + u, jj);
-                char *dp = const_cast<char *>(sp) + delta;
-#pragma unroll
-                for (int u = 0; u < FUP_UNROLL; ++u)
-                    if (u < left) st_stream(reinterpret_cast<double *>(dp + (uint64_t)ldb * u), t[u]);
+                    for (int h = 0; h < NP; ++h)
+                        if (active[h]) t[u][h] = ld_stream(reinterpret_cast<const double *>(sp + (uint64_t)ldb * u + 512 * h));
             }
         }
-        if (++strip == nstrips) { strip = 0; ++rt; }
+        if (__builtin_expect(redo, 0)) {
+#pragma unroll
+            for (int u = 0; u < FUP_UNROLL; ++u)
+#pragma unroll
+                for (int h = 0; h < NP; ++h)
+                    if (active[h])
+                        t[u][h] = guarded_pair(t[u][h], f, s_lvl, my_rows + h * 32, NP * 32, cols + u, 8, i0 + 8 * b + u, jj + 64 * h);
+        }
+        char *dp = const_cast<char *>(sp) + delta;
+#pragma unroll
+        for (int h = 0; h < NP; ++h) {
+            if (active[h]) {
+#pragma unroll
+                for (int u = 0; u < FUP_UNROLL; ++u) st_stream(reinterpret_cast<double *>(dp + (uint64_t)ldb * u + 512 * h), t[u][h]);
+            }
+        }
+        sp += (uint64_t)ldb * FUP_UNROLL;
+    }
+    if (rows & 7) {
+        // the ragged last batch of the table (n + 1 is rarely a multiple of 8): guarded road, multipliers from global
+        const int left = rows & 7, row0 = i0 + 8 * nb;
+        for (int h = 0; h < NP; ++h) {
+            if (!active[h]) continue;
+            for (int u = 0; u < left; ++u) {
+                double2 t = ld_stream(reinterpret_cast<const double *>(sp + (uint64_t)ldb * u + 512 * h));
+                for (int l = 0; l < f; ++l) {
+                    const double2 rj = my_rows[(l * NP + h) * 32];
+                    const LevelDiv L = s_lvl[l];
+                    const double ci = __ldcg(s_colp[l] + row0 + u);
+                    t.x = apply_level(t.x, row0 + u, jj + 64 * h, L, rj.x, ci);
+                    t.y = apply_level(t.y, row0 + u, jj + 64 * h + 1, L, rj.y, ci);
+                }
+                st_stream(reinterpret_cast<double *>(const_cast<char *>(sp) + delta + (uint64_t)ldb * u + 512 * h), t);
+            }
+        }
     }
 }
 
@@ -1241,36 +1275,36 @@ static cudaError_t launch_update_variant(double *A0, double *A1, int n, int m, i
                                          const PlanHeader *plan, const double *ROWS, const double *COLS, int minb,
                                          bool persistent, cudaStream_t stream) {
     if ((int)get_option(SPX_OPT_FUSE_VARIANT) == 1) return cudaErrorNotSupported;
-    int tr = (int)get_option(SPX_OPT_FUSE_TILE_ROWS);
-    if (tr <= 0) tr = 32;
-    if (minb <= 0) minb = 3;
-    int items = (int)get_option(SPX_OPT_FUSE_ITEMS);
-    if (items <= 0) items = 8;
-    const size_t smem = (FUP_THREADS / 32) * sizeof(double) * FUSE_MAX * (LZ_SC + (size_t)tr);      // per warp: rows[F][64] | cols[F][tr]
+    int rw = (int)get_option(SPX_OPT_FUSE_TILE_ROWS);
+    if (rw <= 0) rw = 128;
+    int np = (int)get_option(SPX_OPT_FUSE_PAIRS);
+    if (np <= 0) np = 2;
+    if (minb <= 0) minb = np == 2 ? 3 : 2;
     static bool configured[64] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!configured[dev]) {
-        const int cap = (int)((FUP_THREADS / 32) * sizeof(double) * FUSE_MAX * (LZ_SC + 256));
-        if ((e = cudaFuncSetAttribute(update_lazy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(update_lazy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(update_lazy_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
+#define SPX_LZ_CFG(NP, TH, MB) \
+        if ((e = cudaFuncSetAttribute(update_lazy_kernel<NP, TH, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (TH / 32) * LazyGeom<NP>::WARP_BYTES)) != cudaSuccess) return e;
+        SPX_LZ_CFG(1, 256, 2) SPX_LZ_CFG(1, 256, 3) SPX_LZ_CFG(2, 128, 2) SPX_LZ_CFG(2, 128, 3)
+#undef SPX_LZ_CFG
         configured[dev] = true;
     }
-    const int64_t nitems = (int64_t)((m + LZ_SC - 1) / LZ_SC) * ((n + 1 + tr - 1) / tr);
-    if (m <= 0 || nitems == 0) return cudaSuccess;          // a shard without columns only prices
-    if (nitems + 64 * (FUP_THREADS / 32) >= (int64_t)1 << 31) return cudaErrorInvalidValue;
+    const int sc = 64 * np, wpc = (np == 2) ? 4 : 8;        // strip width, warps per CTA
+    const int64_t nwork = (int64_t)((m + sc - 1) / sc) * ((n + 1 + rw - 1) / rw);      // warp-sized pieces
+    if (m <= 0 || nwork == 0) return cudaSuccess;           // a shard without columns only prices
+    if (nwork + 64 >= (int64_t)1 << 31) return cudaErrorInvalidValue;
     (void)persistent;
-    const int64_t per_cta = (int64_t)(FUP_THREADS / 32) * items;
-    const unsigned grid = (unsigned)((nitems + per_cta - 1) / per_cta);
-    if (minb == 2)
-        update_lazy_kernel<2><<<grid, FUP_THREADS, smem, stream>>>(A0, A1, n, m, ld, cbd, col0, R, tr, items, plan, ROWS, COLS);
-    else if (minb == 4)
-        update_lazy_kernel<4><<<grid, FUP_THREADS, smem, stream>>>(A0, A1, n, m, ld, cbd, col0, R, tr, items, plan, ROWS, COLS);
-    else
-        update_lazy_kernel<3><<<grid, FUP_THREADS, smem, stream>>>(A0, A1, n, m, ld, cbd, col0, R, tr, items, plan, ROWS, COLS);
+    const unsigned grid = (unsigned)((nwork + wpc - 1) / wpc);
+#define SPX_LZ_RUN(NP, TH, MB) \
+    update_lazy_kernel<NP, TH, MB><<<grid, TH, (TH / 32) * LazyGeom<NP>::WARP_BYTES, stream>>>(A0, A1, n, m, ld, cbd, col0, R, \
+                                                                                               rw, plan, ROWS, COLS)
+    if (np == 2) { if (minb == 2) SPX_LZ_RUN(2, 128, 2); else SPX_LZ_RUN(2, 128, 3); }
+    else         { if (minb == 3) SPX_LZ_RUN(1, 256, 3); else SPX_LZ_RUN(1, 256, 2); }
+#undef SPX_LZ_RUN
     spx_host::count_launch();
     return cudaGetLastError();
 }

@@ -29,11 +29,12 @@ class loop_mode:
         if self.name == "fused-gpuwide":               # ... with the whole-GPU cooperative pricing kernel forced on
             assert N.lib().spx_set_option(8, 2) == 0
             return "fused"
-        if isinstance(self.name, str) and self.name.startswith("fused-x"):   # "fused-x<variant>-<tile rows>[-<minb>]":
+        if isinstance(self.name, str) and self.name.startswith("fused-x"):   # "fused-x<variant>-<rows>[-<minb>[-<pairs>]]":
             parts = self.name[len("fused-x"):].split("-")                    # update kernel schedule
             assert N.lib().spx_set_option(10, int(parts[0])) == 0
             assert N.lib().spx_set_option(11, int(parts[1])) == 0
             assert N.lib().spx_set_option(7, int(parts[2]) if len(parts) > 2 else 0) == 0
+            assert N.lib().spx_set_option(12, int(parts[3]) if len(parts) > 3 else 0) == 0
             return "fused"
         return self.name
 
@@ -44,7 +45,7 @@ class loop_mode:
         if self.name == "fused-gpuwide":
             N.lib().spx_set_option(8, 0)
         if isinstance(self.name, str) and self.name.startswith("fused-x"):
-            for k in (10, 11, 7):
+            for k in (10, 11, 7, 12):
                 N.lib().spx_set_option(k, 0)
 
 
@@ -708,9 +709,10 @@ def test_column_sharded_ranks_emulated_entering_column_on_late_ranks(spx, world,
 
 
 # --------------------------------------------------------------------------- fused update kernel schedules
-# "fused-x<variant>-<tile rows>[-<min blocks>]": variant 0 = update_lazy_kernel (the default: ONE range test per cell
-# per pass), 1 = round 1's update_fused_kernel (a range test per cell per level)
-X_MODES = ["fused-x0-32", "fused-x0-64-2", "fused-x0-256-3", "fused-x0-8-4", "fused-x0-40-2", "fused-x1-0", "fused-x1-0-3"]
+# "fused-x<variant>-<rows per warp strip>[-<min blocks>[-<column pairs per lane>]]": variant 0 = update_lazy_kernel (the
+# default: ONE range test per cell per pass), 1 = round 1's update_fused_kernel (a range test per cell per level)
+X_MODES = ["fused-x0-128", "fused-x0-64-2-1", "fused-x0-256-3-2", "fused-x0-8-2-2", "fused-x0-40-2-1", "fused-x0-4096-3-2",
+           "fused-x0-24-3-1", "fused-x1-0", "fused-x1-0-3"]
 
 
 @pytest.mark.parametrize("mode", X_MODES)

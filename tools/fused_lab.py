@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--pivots", type=int, default=400)
     ap.add_argument("--depths", default="1,2,4,8")
     ap.add_argument("--minb", default="3")
-    ap.add_argument("--items", default="0", help="fused update kernel: items per warp (0 = default)")
+    ap.add_argument("--items", default="0", help="fused update kernel: column pairs per lane (0 = default, 1, 2)")
     ap.add_argument("--variants", default="0",
                     help="update kernel schedules as variant:tile_rows, e.g. 0:32,0:64,1 (0 = update_lazy_kernel, the default; "
                          "1 = round 1's update_fused_kernel)")
@@ -60,7 +60,7 @@ def main():
             tr = tab.trace[:npiv].cpu().numpy()
             k = min(len(gold), npiv)
             ok = f" golden[{k}]={'OK' if (tr[:k] == gold[:k]).all() else 'MISMATCH'}"
-        print(f"{mode:9s} F={F} minb={mb} variant={var}:{trows} items={items}: {a.pivots} pivots in {ms:8.2f} ms  {a.pivots / ms * 1e3:8.1f} pivots/s  "
+        print(f"{mode:9s} F={F} minb={mb} variant={var}:{trows} pairs={items}: {a.pivots} pivots in {ms:8.2f} ms  {a.pivots / ms * 1e3:8.1f} pivots/s  "
               f"{ms / a.pivots * 1e3:7.1f} us/pivot  north-star {16.0 * cells * a.pivots / ms / 1e6:8.0f} GB/s  "
               f"status={st} npiv={npiv}{ok}", flush=True)
 
