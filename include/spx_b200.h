@@ -130,7 +130,9 @@ int         spx_selftest_lazy_guard(const double *d_t0, const double *d_p, const
 int spx_import_table(const double *src_rows, const double *src_function, double *d_A, double *d_b,
                      int32_t n, int32_t m, int64_t ld, void *stream);
 /* Column block [col0, col0+m_loc) of the same source -> a local split body
- * d_A[(n+1)][ld_loc] (+ b when d_b != NULL): the loader of one column shard. */
+ * d_A[(n+1)][ld_loc] (+ b when d_b != NULL): the loader of one column shard.
+ * The source pitch is m + 1 cells and b is its column m; m = 0 (with m_loc = 0)
+ * describes the packed block of a rank that owns no columns: b alone, pitch 8 bytes. */
 int spx_import_shard(const double *src_rows, const double *src_function, double *d_A, double *d_b,
                      int32_t n, int32_t m, int64_t col0, int32_t m_loc, int64_t ld_loc,
                      void *stream);

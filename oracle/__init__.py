@@ -57,6 +57,12 @@ def lib() -> ctypes.CDLL:
     L.orc_pick.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                            ctypes.POINTER(ctypes.c_int), dp]
     L.orc_pick.restype = ctypes.c_int
+    L.orc_pick_rule.argtypes = [dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                ctypes.POINTER(ctypes.c_int), dp]
+    L.orc_pick_rule.restype = ctypes.c_int
+    L.orc_solve_rule.argtypes = [dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, i64, ip, dp, ip, ip,
+                                 ctypes.POINTER(i64)]
+    L.orc_solve_rule.restype = ctypes.c_int
     L.orc_update.argtypes = [dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.orc_update.restype = None
     L.orc_init_labels.argtypes = [ip, ip, ctypes.c_int, ctypes.c_int]
@@ -111,10 +117,13 @@ def unflatten(T: np.ndarray, n: int, m: int) -> list[list[float]]:
     return body
 
 
-def pick(T: np.ndarray, n: int, m: int):
+RULES = {"reference": 0, "dantzig": 1}     # "dantzig" is an extension, see spx_oracle.c
+
+
+def pick(T: np.ndarray, n: int, m: int, rule: str = "reference"):
     """simplex.py:70-141 -> (status, r, c, e)."""
     r, c, e = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0.0)
-    st = lib().orc_pick(_dp(T), n, m, ctypes.byref(r), ctypes.byref(c), ctypes.byref(e))
+    st = lib().orc_pick_rule(_dp(T), n, m, RULES[rule], ctypes.byref(r), ctypes.byref(c), ctypes.byref(e))
     return st, r.value, c.value, e.value
 
 
@@ -150,13 +159,14 @@ class Solve(NamedTuple):
     snaps: Optional[np.ndarray]
 
 
-def solve(constraints, function, max_pivots: int = 1_000_000, snapshots: bool = False) -> Solve:
+def solve(constraints, function, max_pivots: int = 1_000_000, snapshots: bool = False,
+          rule: str = "reference") -> Solve:
     T, n, m = flatten(constraints, function)
-    return solve_flat(T, n, m, max_pivots, snapshots)
+    return solve_flat(T, n, m, max_pivots, snapshots, rule=rule)
 
 
 def solve_flat(T0: np.ndarray, n: int, m: int, max_pivots: int = 1_000_000,
-               snapshots: bool = False, keep_trace: bool = True) -> Solve:
+               snapshots: bool = False, keep_trace: bool = True, rule: str = "reference") -> Solve:
     T = np.array(T0, dtype=np.float64, copy=True)
     cells = n_cells(n, m)
     function = T[n * (m + 1):].copy()
@@ -165,8 +175,8 @@ def solve_flat(T0: np.ndarray, n: int, m: int, max_pivots: int = 1_000_000,
     snaps = np.empty((max_pivots + 1, cells), dtype=np.float64) if snapshots else None
     rowlab, collab = init_labels(n, m)
     npiv = ctypes.c_int64(0)
-    st = lib().orc_solve(_dp(T), _dp(scratch), n, m, max_pivots, _ip(trace), _dp(snaps),
-                         _ip(rowlab), _ip(collab), ctypes.byref(npiv))
+    st = lib().orc_solve_rule(_dp(T), _dp(scratch), n, m, RULES[rule], max_pivots, _ip(trace), _dp(snaps),
+                              _ip(rowlab), _ip(collab), ctypes.byref(npiv))
     k = npiv.value
     x = np.zeros(m, dtype=np.float64)
     o2, om = ctypes.c_double(0.0), ctypes.c_double(0.0)

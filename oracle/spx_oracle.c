@@ -19,6 +19,13 @@
  *   orc_solve   : the driving loop      simplex.py:179-199 / :261-269
  *   orc_extract : find_optimum(), f()   simplex.py:48-68  (generalised to m vars)
  *
+ * Extension rule (NOT reference behaviour): orc_pick_rule / orc_solve_rule with
+ * rule = ORC_RULE_DANTZIG replace ONLY the entering-column choice of simplex.py:94-98 (first negative
+ * f cell) by "the most negative f cell, lowest index on ties" — the rule BASELINE.json's north star
+ * words; phase 1 (:72-91), the ratio scan (:107-136) and the pivot arithmetic are the reference's.
+ * There is no reference implementation to pin it against: tests/test_oracle.py checks it against an
+ * independent pure-Python statement of the same rule built on the reference's own ratio scan.
+ *
  * Data layout ("reference flat"): the reference's ragged list-of-lists
  * flattened row-major: rows 0..n-1 have m+1 cells [a_1..a_m, b], then the
  * f row with exactly m cells (simplex.py:36-39).  cells = n*(m+1)+m.
@@ -49,8 +56,11 @@
 
 static inline size_t row_off(int i, int m) { return (size_t)i * (size_t)(m + 1); }
 
-/* simplex.py:70-141, statement by statement. */
-int orc_pick(const double *T, int n, int m, int *r_out, int *c_out, double *e_out)
+#define ORC_RULE_REFERENCE 0   /* first negative f cell, simplex.py:94-98 */
+#define ORC_RULE_DANTZIG   1   /* most negative f cell, lowest index on ties (extension) */
+
+/* simplex.py:70-141, statement by statement; `rule` only changes the entering column (:94-98). */
+int orc_pick_rule(const double *T, int n, int m, int rule, int *r_out, int *c_out, double *e_out)
 {
     int target_row = -1, target_col = -1;
 
@@ -70,8 +80,14 @@ int orc_pick(const double *T, int n, int m, int *r_out, int *c_out, double *e_ou
 
     /* :94-98  first negative cell of the f row (m cells, no constant) */
     const double *f = T + row_off(n, m);
-    for (int j = 0; j < m; ++j)
-        if (f[j] < 0) { target_col = j; break; }
+    if (rule == ORC_RULE_DANTZIG) {
+        /* extension: the most negative cell; '<' keeps the lowest index on ties; NaN never enters */
+        for (int j = 0; j < m; ++j)
+            if (f[j] < 0 && (target_col < 0 || f[j] < f[target_col])) target_col = j;
+    } else {
+        for (int j = 0; j < m; ++j)
+            if (f[j] < 0) { target_col = j; break; }
+    }
     if (target_col < 0) return ORC_OPTIMAL;                      /* :101-103 */
 
     /* :107-136  the sequential ratio scan, kept as the state machine it is */
@@ -90,6 +106,11 @@ int orc_pick(const double *T, int n, int m, int *r_out, int *c_out, double *e_ou
     *r_out = target_row; *c_out = target_col;
     *e_out = T[row_off(target_row, m) + target_col];
     return ORC_PIVOT;                                            /* :141 */
+}
+
+int orc_pick(const double *T, int n, int m, int *r_out, int *c_out, double *e_out)
+{
+    return orc_pick_rule(T, n, m, ORC_RULE_REFERENCE, r_out, c_out, e_out);
 }
 
 /* simplex.py:155-175: out of place, every read from the old table. */
@@ -154,9 +175,9 @@ void orc_extract(const double *T, int n, int m, const int32_t *collab,
  *            simplex.py:181,198)
  * returns the final status; *npiv_out = pivots done.
  */
-int orc_solve(double *T, double *scratch, int n, int m, int64_t max_pivots,
-              int32_t *trace, double *snaps, int32_t *rowlab, int32_t *collab,
-              int64_t *npiv_out)
+int orc_solve_rule(double *T, double *scratch, int n, int m, int rule, int64_t max_pivots,
+                   int32_t *trace, double *snaps, int32_t *rowlab, int32_t *collab,
+                   int64_t *npiv_out)
 {
     const size_t cells = (size_t)n * (size_t)(m + 1) + (size_t)m;
     double *cur = T, *nxt = scratch;
@@ -165,7 +186,7 @@ int orc_solve(double *T, double *scratch, int n, int m, int64_t max_pivots,
     if (snaps) memcpy(snaps, cur, cells * sizeof(double));
     for (;;) {
         int r = 0, c = 0; double e = 0;
-        status = orc_pick(cur, n, m, &r, &c, &e);
+        status = orc_pick_rule(cur, n, m, rule, &r, &c, &e);
         if (status != ORC_PIVOT) break;
         if (k >= max_pivots) { status = ORC_CAP; break; }
         if (trace) { trace[2 * k] = r; trace[2 * k + 1] = c; }
@@ -178,6 +199,13 @@ int orc_solve(double *T, double *scratch, int n, int m, int64_t max_pivots,
     if (cur != T) memcpy(T, cur, cells * sizeof(double));
     *npiv_out = k;
     return status;
+}
+
+int orc_solve(double *T, double *scratch, int n, int m, int64_t max_pivots,
+              int32_t *trace, double *snaps, int32_t *rowlab, int32_t *collab,
+              int64_t *npiv_out)
+{
+    return orc_solve_rule(T, scratch, n, m, ORC_RULE_REFERENCE, max_pivots, trace, snaps, rowlab, collab, npiv_out);
 }
 
 /*

@@ -21,6 +21,7 @@ LOOP_MODES = {None: LOOP_AUTO, "auto": LOOP_AUTO, False: LOOP_CLASSIC, "classic"
 PIVOT, OPTIMAL, INCORRECT, NOCONV, CAP, PEER_TIMEOUT = 1, 0, -1, -2, -3, -4
 RULE_REFERENCE, RULE_DANTZIG = 0, 1
 OPT_UPDATE_KERNEL, OPT_TILED_MIN_BLOCKS, OPT_PIPE_ORDER, OPT_PIPE_GRID, OPT_TILED_ROWS, OPT_FUSE_DEPTH = 1, 2, 3, 4, 5, 6
+OPT_FUSE_MIN_BLOCKS, OPT_FUSE_PRICING, OPT_FUSE_LOOKAHEAD, OPT_FUSE_VARIANT, OPT_FUSE_TILE_ROWS, OPT_FUSE_PAIRS = 7, 8, 9, 10, 11, 12
 RULES = {"reference": RULE_REFERENCE, "bland": RULE_REFERENCE, "dantzig": RULE_DANTZIG}
 
 # the two ValueError texts of pick_element(), /root/reference/src/simplex.py:89,139

@@ -178,8 +178,9 @@ int spx_selftest_lazy_guard(const double *d_t0, const double *d_p, const double 
 // ---- layout conversion ---------------------------------------------------------
 int spx_import_shard(const double *src_rows, const double *src_function, double *d_A, double *d_b,
                      int32_t n, int32_t m, int64_t col0, int32_t m_loc, int64_t ld_loc, void *stream) {
-    SPX_REQUIRE(src_rows && src_function && d_A, "spx_import_shard: null pointer");
-    SPX_REQUIRE(n >= 0 && m >= 1 && m_loc >= 0 && col0 >= 0 && col0 + m_loc <= m,
+    SPX_REQUIRE(src_rows && (src_function || m_loc == 0) && d_A, "spx_import_shard: null pointer");
+    // m == 0 is a packed block of a rank that owns no columns: rows of ONE cell, the b column (pitch 8 bytes)
+    SPX_REQUIRE(n >= 0 && (m >= 1 || (m == 0 && m_loc == 0)) && m_loc >= 0 && col0 >= 0 && col0 + m_loc <= m,
                 "spx_import_shard: bad shape n=%d m=%d col0=%lld m_loc=%d", n, m, (long long)col0, m_loc);
     SPX_REQUIRE(ld_loc >= m_loc && ld_loc % 16 == 0, "spx_import_shard: ld=%lld must be a multiple of 16 >= m_loc",
                 (long long)ld_loc);

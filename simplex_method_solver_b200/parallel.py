@@ -235,7 +235,8 @@ class ShardedTableau:
         assert block.shape == (self.n, self.m_loc + 1) and block.dtype == np.float64 and block.flags.c_contiguous
         fb = np.ascontiguousarray(function_block, dtype=np.float64)
         assert fb.shape == (self.m_loc,)
-        self.ops.import_shard(block, fb, self.A[0], self.b[0], self.n, max(self.m_loc, 1), 0, self.m_loc, self.ld)
+        # the packed block's own width is its source pitch: m_loc columns + the b column (m_loc == 0: b alone)
+        self.ops.import_shard(block, fb, self.A[0], self.b[0], self.n, self.m_loc, 0, self.m_loc, self.ld)
         self.ops.init_state(self.state, self.rowlab, self.collab, self.n, self.m, int(max_pivots))
         self.npiv_enqueued = 0
         self.si, self.priced = 0, False

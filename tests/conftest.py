@@ -39,3 +39,11 @@ def reference_module():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+@pytest.fixture(scope="session")
+def dantzig_cases():
+    """The extension entering rule (most negative, lowest index on ties), driven through the reference itself by
+    tests/golden/make_golden.py dantzig."""
+    with open(os.path.join(GOLDEN, "dantzig_cases.json")) as fh:
+        return json.load(fh)["cases"]

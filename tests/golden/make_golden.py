@@ -280,6 +280,101 @@ def make_cfg5():
         print(f"km{n}:", len(trace), "pivots", d[f"km{n}"]["seconds"], "s")
 
 
+def drive_dantzig(rows, c, cap):
+    """The extension rule 'most negative f cell, lowest index on ties'  driven THROUGH THE
+    REFERENCE: outside phase 1 the chosen column is swapped into position 0 of the reference's own table, where its
+    first-negative rule (simplex.py:94-98) must take it; pick_element() / recalculate_matrix() then run unmodified
+    (ratio scan, arithmetic, label swap) and the columns are swapped back.  Cell arithmetic does not depend on the
+    column order, so the result is the reference's own arithmetic under the other entering rule."""
+    sm = ref.SimplexMethod([[float(v) for v in r] for r in rows], [float(v) for v in c])
+    n, m = sm.n, sm.m
+    trace = []
+
+    def swap(j):
+        if j == 0:
+            return
+        for row in sm.table:
+            row[0], row[j] = row[j], row[0]
+        sm.row[0], sm.row[j] = sm.row[j], sm.row[0]
+
+    try:
+        while True:
+            phase1 = any(sm.table[i][m] < 0 for i in range(n))
+            f = sm.table[n]
+            j = 0
+            if not phase1:
+                best = None
+                for q in range(m):
+                    if f[q] < 0 and (best is None or f[q] < f[best]):
+                        best = q
+                j = best if best is not None else 0
+            swap(j)
+            try:
+                ok, i, jj, e = sm.pick_element()
+                if not ok:
+                    swap(j)
+                    return sm, trace, "optimal", (i, jj, e)
+                if len(trace) >= cap:
+                    swap(j)
+                    return sm, trace, "cap", None
+                if not phase1:
+                    assert jj == 0
+                    jj_true = j
+                else:
+                    jj_true = jj
+                trace.append([i, jj_true])
+                sm.recalculate_matrix()
+            finally:
+                pass
+            swap(j)
+    except ValueError as e:
+        swap(j)
+        return sm, trace, str(e), None
+
+
+def make_dantzig():
+    """Fixtures of the Dantzig extension rule, produced by the reference itself (see drive_dantzig)."""
+    cases = []
+    rng = np.random.default_rng(20261019)
+    for t in range(150):
+        n = int(rng.integers(1, 10))
+        m = int(rng.integers(2, 7))
+        fam = t % 3
+        if fam == 0:
+            A = np.round(rng.uniform(-50, 50, (n, m)), 2)
+            b = np.round(rng.uniform(-500, 2000, n), 2)
+            c = np.round(rng.uniform(-3, 3, m), 2)
+        elif fam == 1:
+            A = rng.integers(-3, 4, (n, m)).astype(float)
+            b = rng.integers(-2, 7, n).astype(float)
+            c = rng.integers(-3, 4, m).astype(float)
+        else:
+            A = -rng.uniform(0.1, 1, (n, m))
+            b = rng.uniform(1, 2, n)
+            c = -rng.uniform(0.1, 1, m)
+        rows = np.hstack([A, b[:, None]]).tolist()
+        sm, trace, end, fin = drive_dantzig(rows, c.tolist(), 200)
+        cases.append({"name": f"dantzig_{['gui2dp', 'smallint', 'dense'][fam]}_{t:03d}", "provenance": "reference",
+                      "rows": [[hx(v) for v in r] for r in rows], "c": [hx(v) for v in c], "cap": 200, "end": end,
+                      "trace": trace, "final_table_sha256": table_sha(sm.table),
+                      "row_labels": list(sm.row), "column_labels": list(sm.column)})
+    for (n, m, seed) in [(30, 40, 1), (64, 33, 2), (17, 96, 3), (40, 700, 4)]:
+        rows, c = W.dense_lp(n, m, seed)
+        sm, trace, end, fin = drive_dantzig(rows.tolist(), c.tolist(), 400)
+        cases.append({"name": f"dantzig_dense_{n}x{m}_seed{seed}", "provenance": "reference",
+                      "generator": {"kind": "dense_lp", "n": n, "m": m, "seed": seed}, "cap": 400, "end": end,
+                      "trace": trace, "final_table_sha256": table_sha(sm.table),
+                      "row_labels": list(sm.row), "column_labels": list(sm.column)})
+    with open(os.path.join(HERE, "dantzig_cases.json"), "w") as fh:
+        json.dump({"made_by": "tests/golden/make_golden.py dantzig", "rule": "most negative f cell, lowest index on ties "
+                   "(extension; entering column only), driven through the reference by a column swap", "cases": cases},
+                  fh, indent=0)
+    ends = {}
+    for cc in cases:
+        ends[cc["end"]] = ends.get(cc["end"], 0) + 1
+    print("dantzig:", len(cases), "cases", ends)
+
+
 def make_cfg4():
     """16384 x 32768 prefix via the oracle (the reference cannot hold this shape)."""
     import ctypes
@@ -324,4 +419,4 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["small"]
     for w in what:
         {"small": make_small, "cfg2": make_cfg2, "cfg3": make_cfg3, "cfg5": make_cfg5,
-         "cfg4": make_cfg4}[w]()
+         "cfg4": make_cfg4, "dantzig": make_dantzig}[w]()

@@ -85,14 +85,17 @@ def test_options_validate_their_ranges(native):
     L = native.load()
     try:
         assert L.spx_get_option(10) == 0 and L.spx_get_option(11) == 0 and L.spx_get_option(7) == 0   # defaults
-        assert L.spx_set_option(10, 3) == 0 and L.spx_get_option(10) == 3
-        assert L.spx_set_option(10, 8) != 0 and L.spx_set_option(10, -1) != 0
-        assert L.spx_set_option(11, 40) == 0 and L.spx_get_option(11) == 40
-        assert L.spx_set_option(11, 12) != 0 and L.spx_set_option(11, 264) != 0
+        assert L.spx_get_option(12) == 0
+        assert L.spx_set_option(10, 1) == 0 and L.spx_get_option(10) == 1          # round 1's fused update kernel
+        assert L.spx_set_option(10, 2) != 0 and L.spx_set_option(10, -1) != 0
+        assert L.spx_set_option(11, 40) == 0 and L.spx_get_option(11) == 40        # rows per warp strip: multiples of 8
+        assert L.spx_set_option(11, 12) != 0 and L.spx_set_option(11, 4104) != 0
+        assert L.spx_set_option(12, 2) == 0 and L.spx_set_option(12, 3) != 0       # column pairs per lane: 1 or 2
         assert L.spx_set_option(6, 9) != 0 and L.spx_set_option(99, 0) != 0
     finally:
         L.spx_set_option(10, 0)
         L.spx_set_option(11, 0)
+        L.spx_set_option(12, 0)
 
 
 def test_argument_validation_reports_text(native):

@@ -234,15 +234,61 @@ def test_lookahead_state_feeds_the_step_api_and_resumes(spx, mode):
     assert sol.x.tobytes() == ref.x.tobytes()
 
 
-@pytest.mark.parametrize("lookahead", [False, True, "resident", "fused"])
-def test_dantzig_rule_modes_agree(spx, lookahead):
-    """rule='dantzig' (extension, not reference behaviour): classic and look-ahead give one trace."""
-    rows, c = W.dense_lp(30, 50, 4)
-    a = spx.simplex.SimplexMethod(rows, c, engine="stream", rule="dantzig").solve(max_pivots=500, chunk=9,
-                                                                                  lookahead=lookahead)
-    b = spx.batched.solve_batched(flat_of(rows, c)[None, :], 30, 50, max_pivots=500, rule="dantzig")
-    assert a.status == b.status[0] == 0 and a.npiv == b.npiv[0]
-    assert a.trace.tolist() == b.trace[0, : a.npiv].tolist()
+@pytest.mark.parametrize("lookahead", [False, True, "resident", "fused", "fused-coop", "fused-gpuwide", "warp"])
+def test_dantzig_rule_every_loop_against_the_restated_oracle(spx, dantzig_cases, lookahead):
+    """rule='dantzig' (extension: most negative f cell, lowest index on ties) in every CUDA loop —
+    classic, look-ahead, L2-resident, fused (one-CTA, cooperative, whole-GPU pricing), warp-resident batched —
+    against fixtures the reference itself produced under that rule (tests/golden/make_golden.py::drive_dantzig) and,
+    for a mid-size LP, against the oracle's restatement (oracle.solve(rule="dantzig"))."""
+    if lookahead == "warp":
+        for case in dantzig_cases:
+            rows, c = case_inputs(case)
+            n, m = rows.shape[0], rows.shape[1] - 1
+            if n * (m + 1) + m > spx.N.load().spx_batched_max_cells():
+                continue                                  # larger than a CTA-resident LP: the streaming loops cover it
+            res = spx.batched.solve_batched(flat_of(rows, c)[None, :], n, m, max_pivots=case["cap"], rule="dantzig")
+            assert int(res.status[0]) == END_TO_STATUS[case["end"]], case["name"]
+            assert res.trace[0, : int(res.npiv[0])].tolist() == case["trace"], case["name"]
+            assert table_sha(res.tables[0]) == case["final_table_sha256"], case["name"]
+        return
+    with loop_mode(lookahead) as mode_:
+        for case in dantzig_cases:
+            rows, c = case_inputs(case)
+            sm = spx.simplex.SimplexMethod(rows, c, engine="stream", rule="dantzig")
+            sol = sm.solve(max_pivots=case["cap"], chunk=7, lookahead=mode_)
+            assert sol.status == END_TO_STATUS[case["end"]], case["name"]
+            assert sol.trace.tolist() == case["trace"], case["name"]
+            assert table_sha(sm._dev.export_flat(sm._npiv)) == case["final_table_sha256"], case["name"]
+            assert sm.row == case["row_labels"] and sm.column == case["column_labels"], case["name"]
+        rows, c = W.dense_lp(130, 1030, 9)
+        o = oracle.solve(rows, c, max_pivots=300, rule="dantzig")
+        sm = spx.simplex.SimplexMethod(rows, c, engine="stream", rule="dantzig")
+        sol = sm.solve(max_pivots=300, chunk=11, lookahead=mode_)
+        assert (sol.status, sol.npiv) == (o.status, o.npiv)
+        assert sol.trace.tolist() == o.trace.tolist()
+        assert np.array_equal(bits(sm._dev.export_flat(sm._npiv)), bits(o.table))
+
+
+def test_print_table_matches_the_reference_format(spx, capsys):
+    """print_table() (simplex.py:41-46): a tab-separated header of the row labels, then one line per table row led by
+    its column label, cells rounded to 6 places — before and after a pivot."""
+    rows, c = [[-1.0, -1.0, 10.0], [1.0, -2.0, 4.0], [0.5, 0.25, -1.0 / 3.0]], [-1.0, -5.0]
+    sm = spx.simplex.SimplexMethod(rows, c)
+
+    def expected(table, row, column):
+        out = "\t" + "\t".join(row) + "\n"
+        for k in range(len(table)):
+            out += column[k] + "\t" + "\t".join(str(round(v, 6)) for v in table[k]) + "\n"
+        return out
+
+    sm.print_table()
+    assert capsys.readouterr().out == expected(rows + [c], ['x1', 'x2', '-b'], ['y1', 'y2', 'y3', 'f'])
+    sm.recalculate_matrix()
+    o = oracle.solve(rows, c, max_pivots=1)
+    tab = oracle.unflatten(o.table, 3, 2)
+    rl, cl = oracle.label_strings(o.rowlab, o.collab, 2)
+    sm.print_table()
+    assert capsys.readouterr().out == expected(tab, rl, cl)
 
 
 def test_inputs_not_mutated_and_attributes(spx):

@@ -257,3 +257,49 @@ def test_lazy_replay_of_pending_pivots_is_bit_identical():
                     got = lazy(t, j, upto)
                     assert bits(np.array([got]))[0] == bits(np.array([want]))[0] or (np.isnan(got) and np.isnan(want)), \
                         (trial, upto, t, j, got, want)
+
+
+# --------------------------------------------------------------------------- the extension entering rule (N4)
+def test_dantzig_rule_golden_cases(dantzig_cases):
+    """rule="dantzig" of the oracle (most negative f cell, lowest index on ties; everything else the reference's)
+    against fixtures the REFERENCE produced under that rule (make_golden.py::drive_dantzig swaps the chosen column
+    into position 0, where the reference's own first-negative rule takes it)."""
+    assert len(dantzig_cases) >= 150
+    differs = 0
+    for case in dantzig_cases:
+        rows, c = case_inputs(case)
+        m = rows.shape[1] - 1
+        o = oracle.solve(rows, c, max_pivots=case["cap"], rule="dantzig")
+        assert o.status == END_TO_STATUS[case["end"]], case["name"]
+        assert o.trace.tolist() == case["trace"], case["name"]
+        assert table_sha(o.table) == case["final_table_sha256"], case["name"]
+        rl, cl = oracle.label_strings(o.rowlab, o.collab, m)
+        assert rl == case["row_labels"] and cl == case["column_labels"], case["name"]
+        differs += oracle.solve(rows, c, max_pivots=case["cap"]).trace.tolist() != case["trace"]
+    assert differs >= 30                      # the rule really is a different rule on these LPs
+
+
+def test_dantzig_rule_equals_reference_driven_by_column_swap(reference_module):
+    """Fresh LPs (not in the fixtures) through the live reference under the extension rule."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    rng = np.random.default_rng(77)
+    for t in range(90):
+        n, m = int(rng.integers(1, 12)), int(rng.integers(2, 9))
+        if t % 3 == 0:
+            A, b, c = (np.round(rng.uniform(-50, 50, (n, m)), 2), np.round(rng.uniform(-500, 2000, n), 2),
+                       np.round(rng.uniform(-3, 3, m), 2))
+        elif t % 3 == 1:
+            A, b, c = (rng.integers(-3, 4, (n, m)).astype(float), rng.integers(-2, 7, n).astype(float),
+                       rng.integers(-3, 4, m).astype(float))
+        else:
+            A, b, c = -rng.uniform(0.1, 1, (n, m)), rng.uniform(1, 2, n), -rng.uniform(0.1, 1, m)
+        rows = np.hstack([A, b[:, None]])
+        sm, trace, end, _ = mg.drive_dantzig(rows.tolist(), c.tolist(), 150)
+        o = oracle.solve(rows, c, max_pivots=150, rule="dantzig")
+        assert o.status == END_TO_STATUS[end] and o.trace.tolist() == trace, t
+        assert table_sha(o.table) == mg.table_sha(sm.table), t

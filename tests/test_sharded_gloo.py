@@ -51,7 +51,7 @@ def test_column_block_alignment():
     assert P.column_block(32768, 3, 8) == (3 * 4096, 4096)
 
 
-def _sharded_worker(rank, world, port, n, m, seed, cap, kind, lookahead, out):
+def _sharded_worker(rank, world, port, n, m, seed, cap, kind, lookahead, out, local=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -59,7 +59,13 @@ def _sharded_worker(rank, world, port, n, m, seed, cap, kind, lookahead, out):
         rows, c = _make_lp(n, m, seed, kind)
         sh = P.ShardedTableau(n, m, rank, world, device="cpu", trace_capacity=cap, ops=CpuShardOps(),
                               lookahead=lookahead)
-        sh.load(rows, c, max_pivots=cap)
+        if local:
+            # every rank packs ITS OWN block [n, m_loc + 1] (its columns, then b): the e2e path of bench.py at N > 1;
+            # a rank without columns (m_loc == 0) packs the b column alone
+            blk = np.ascontiguousarray(np.hstack([rows[:, sh.col0: sh.col0 + sh.m_loc], rows[:, m: m + 1]]))
+            sh.load_local(blk, np.ascontiguousarray(c[sh.col0: sh.col0 + sh.m_loc]), max_pivots=cap)
+        else:
+            sh.load(rows, c, max_pivots=cap)
         status, npiv = sh.solve(cap, check_every=5)
         body = sh.local_body().numpy().copy()
         res = {"status": status, "npiv": npiv, "trace": sh.trace[:npiv].numpy().copy(),
@@ -76,11 +82,11 @@ def _make_lp(n, m, seed, kind):
     return make_lp(n, m, seed, kind)
 
 
-def _run_world(world, n, m, seed, cap, kind, lookahead):
+def _run_world(world, n, m, seed, cap, kind, lookahead, local=False):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, n, m, seed, cap, kind, lookahead, out))
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, n, m, seed, cap, kind, lookahead, out, local))
              for r in range(world)]
     for p in procs:
         p.start()
@@ -99,11 +105,24 @@ def _run_world(world, n, m, seed, cap, kind, lookahead):
     (3, 64, 1600, "late", 7),        # entering columns on ranks 1 and 2, ~30 owner changes in 60 pivots
 ])
 def test_sharded_trace_equals_single_process_oracle(world, n, m, kind, seed, lookahead):
+    _check_world(world, n, m, kind, seed, lookahead, local=False)
+
+
+@pytest.mark.parametrize("world,n,m,kind,seed", [
+    (2, 9, 40, "smallint", 8),       # fewer tiles than ranks: rank 1 packs a block WITHOUT columns (b alone)
+    (3, 12, 600, "dense", 5),        # 2 tiles over 3 ranks: rank 2 owns nothing
+    (2, 24, 1100, "late", 3),
+])
+def test_sharded_load_local_packed_blocks(world, n, m, kind, seed):
+    _check_world(world, n, m, kind, seed, lookahead=True, local=True)
+
+
+def _check_world(world, n, m, kind, seed, lookahead, local):
     import oracle
     cap = 60
     rows, c = _make_lp(n, m, seed, kind)
     o = oracle.solve(rows, c, max_pivots=cap)
-    got = _run_world(world, n, m, seed, cap, kind, lookahead)
+    got = _run_world(world, n, m, seed, cap, kind, lookahead, local)
     body = np.zeros((n + 1, m))
     for r in range(world):
         g = got[r]
