@@ -87,6 +87,12 @@ def golden_cfg4():
     return g["input_sha256"], trace, {int(k): v for k, v in marks.items()}
 
 
+def as_i64(v: int) -> int:
+    """An unsigned 64-bit checksum as the int64 a torch tensor holds (same bits; sums wrap the same way)."""
+    v &= 0xFFFFFFFFFFFFFFFF
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
 def check_against_marks(trace_np, need, marks, gold, table_at_need=None):
     """Assert the run's pivot sequence against the golden trace (all `need` pivots when the golden is that long) and,
     when `need` is a mark, the table digests.  Returns the parity string of the JSON line."""
@@ -557,11 +563,12 @@ def late_lp_preflight(FusedCls, rank, world, dev, dist):
     blocks = [column_block(m, r, world) for r in range(world)]
     own = [next(k for k, (a, w) in enumerate(blocks) if a <= int(cc) < a + w) for _, cc in gold]
     changes = sum(1 for a, b in zip(own, own[1:]) if a != b)
-    why, sh = "", None
+    # local work first (anything may fail on ONE rank), then the same collectives on EVERY rank whatever happened
+    why, sh, ck_local, f_local, b_sha = "", None, 0, b"", ""
     try:
         sh = FusedCls(n, m, rank, world, device=dev, trace_capacity=cap + 64, depth=fused_depth_for(world))
         sh.load(rows, c, max_pivots=cap + 64)
-        status, npiv = sh.solve(cap + 64, check_every=64)
+        sh.solve(cap + 64, check_every=64)
         st = sh.sync()
         if (int(st.status), int(st.npiv)) != (g["status"], g["npiv"]):
             why = f"late LP ended with status {st.status} after {st.npiv} pivots, golden {g['status']} after {g['npiv']}"
@@ -569,19 +576,9 @@ def late_lp_preflight(FusedCls, rank, world, dev, dist):
             why = "late LP: pivot sequence differs from the oracle's"
         else:
             body = sh.local_body()
-            ck = torch.tensor([W.body_checksum_torch(body[:n], m_total=m, col0=sh.col0) if sh.m_loc else 0],
-                              dtype=torch.int64, device=dev)
-            dist.all_reduce(ck)
+            ck_local = as_i64(W.body_checksum_torch(body[:n], m_total=m, col0=sh.col0)) if sh.m_loc else 0
             f_local = body[n].cpu().numpy().tobytes()
-            fs = [None] * world
-            dist.all_gather_object(fs, f_local)
             b_sha = hashlib.sha256(sh.b_current().cpu().numpy().tobytes()).hexdigest()
-            if (int(ck.item()) & 0xFFFFFFFFFFFFFFFF) != int(g["body_checksum_u64"]):
-                why = "late LP: body checksum differs from the oracle's"
-            elif hashlib.sha256(b"".join(fs)).hexdigest() != g["f_sha256"]:
-                why = "late LP: f row differs from the oracle's"
-            elif b_sha != g["b_sha256"]:
-                why = "late LP: b column differs from the oracle's"
     except Exception as e:                               # noqa: BLE001 - reported, then the documented fallback
         why = f"{type(e).__name__}: {e}"
     finally:
@@ -590,6 +587,17 @@ def late_lp_preflight(FusedCls, rank, world, dev, dist):
                 sh.close()
             except Exception:                            # noqa: BLE001
                 pass
+    ck = torch.tensor([ck_local], dtype=torch.int64, device=dev)
+    dist.all_reduce(ck)
+    fs = [None] * world
+    dist.all_gather_object(fs, f_local)
+    if not why:
+        if (int(ck.item()) & 0xFFFFFFFFFFFFFFFF) != int(g["body_checksum_u64"]):
+            why = "late LP: body checksum differs from the oracle's"
+        elif hashlib.sha256(b"".join(fs)).hexdigest() != g["f_sha256"]:
+            why = "late LP: f row differs from the oracle's"
+        elif b_sha != g["b_sha256"]:
+            why = "late LP: b column differs from the oracle's"
     okf = torch.tensor([0 if why else 1], dtype=torch.int32, device=dev)
     dist.all_reduce(okf, op=dist.ReduceOp.MIN)
     return int(okf.item()) == 1, changes, why
@@ -612,7 +620,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that fails an assertion must not leave its peers in a collective for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     N.lib()
     peak, peak_src = measured_peak()
     in_sha, gold, marks = golden_cfg4()
@@ -880,7 +890,7 @@ def run_ours(args):
         else:
             cur = int(st.npiv) & 1
             body, bcur = sh.A[cur, :, : sh.m_loc], sh.b[cur, :N_ROWS]
-        ck = torch.tensor([W.body_checksum_torch(body[:N_ROWS], m_total=M_COLS, col0=sh.col0) if sh.m_loc else 0],
+        ck = torch.tensor([as_i64(W.body_checksum_torch(body[:N_ROWS], m_total=M_COLS, col0=sh.col0)) if sh.m_loc else 0],
                           dtype=torch.int64, device=dev)
         dist.all_reduce(ck)
         fs = [None] * world

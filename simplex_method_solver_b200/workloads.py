@@ -137,15 +137,18 @@ def body_checksum_numpy(body: np.ndarray) -> int:
     return int(acc)
 
 
-def body_checksum_torch(body) -> int:
-    """Same checksum for a device tensor view [n, m] (fp64, any row stride); int64 wraps mod 2^64."""
+def body_checksum_torch(body, m_total=None, col0: int = 0) -> int:
+    """Same checksum for a device tensor view [n, m_loc] (fp64, any row stride); int64 wraps mod 2^64.
+    A column shard passes the width of the whole table (m_total) and its first column (col0): the checksums of the
+    shards then ADD UP (mod 2^64) to the checksum of the whole body."""
     import torch
     n, m = body.shape
+    mt = int(m if m_total is None else m_total)
     dev = body.device
-    j2 = torch.arange(m, dtype=torch.int64, device=dev) * 2 + 1
+    j2 = (torch.arange(m, dtype=torch.int64, device=dev) + int(col0)) * 2 + 1
     acc = torch.zeros((), dtype=torch.int64, device=dev)
     for i0 in range(0, n, 1024):
         blk = body[i0:i0 + 1024].contiguous().view(torch.int64)
-        base = (torch.arange(i0, i0 + blk.shape[0], dtype=torch.int64, device=dev) * (2 * m))[:, None]
+        base = (torch.arange(i0, i0 + blk.shape[0], dtype=torch.int64, device=dev) * (2 * mt))[:, None]
         acc = acc + (blk * (base + j2[None, :])).sum()
     return int(acc.item()) & 0xFFFFFFFFFFFFFFFF

@@ -375,6 +375,36 @@ def make_dantzig():
     print("dantzig:", len(cases), "cases", ends)
 
 
+def make_late():
+    """The multi-GPU preflight LP of bench.py (N > 1): tests/util.py::make_lp(96, 4096, 7, "late") — dense_lp with a
+    positive objective on the first 95 % of the columns, so the entering column starts on the LAST column block and
+    changes owner rank > 100 times on 2 / 4 / 8 ranks.  Provenance "oracle" (549 pivots of a 96 x 4096 table: ~20 min of
+    the pure-Python reference); tests/test_oracle.py pins the oracle to the live reference on this LP family."""
+    import oracle
+    from simplex_method_solver_b200.parallel import column_block
+    n, m, seed = 96, 4096, 7
+    rows, c = W.dense_lp(n, m, seed)
+    c[: int(0.95 * m)] = np.abs(c[: int(0.95 * m)])
+    o = oracle.solve(rows, c, max_pivots=100000)
+    body = o.table[: n * (m + 1)].reshape(n, m + 1)
+    changes = {}
+    for world in (2, 4, 8):
+        blocks = [column_block(m, r, world) for r in range(world)]
+        own = [next(k for k, (a, w) in enumerate(blocks) if a <= int(cc) < a + w) for _, cc in o.trace]
+        changes[str(world)] = sum(1 for a, b in zip(own, own[1:]) if a != b)
+    out = {"made_by": "tests/golden/make_golden.py late", "provenance": "oracle",
+           "generator": "tests/util.py::make_lp(n, m, seed, 'late')", "n": n, "m": m, "seed": seed,
+           "input_sha256": W.input_digest(rows, c), "status": int(o.status), "npiv": int(o.npiv),
+           "trace": o.trace.tolist(), "pivot_sha256": W.pivot_digest(o.trace),
+           "b_sha256": hashlib.sha256(np.ascontiguousarray(body[:, m]).tobytes()).hexdigest(),
+           "f_sha256": hashlib.sha256(o.table[n * (m + 1):].tobytes()).hexdigest(),
+           "body_checksum_u64": int(W.body_checksum_numpy(body[:, :m])),
+           "owner_changes": changes}
+    with open(os.path.join(HERE, "late_lp.json"), "w") as fh:
+        json.dump(out, fh)
+    print("late:", o.status, o.npiv, changes)
+
+
 def make_cfg4():
     """16384 x 32768 prefix via the oracle (the reference cannot hold this shape)."""
     import ctypes
@@ -419,4 +449,4 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["small"]
     for w in what:
         {"small": make_small, "cfg2": make_cfg2, "cfg3": make_cfg3, "cfg5": make_cfg5,
-         "cfg4": make_cfg4, "dantzig": make_dantzig}[w]()
+         "cfg4": make_cfg4, "dantzig": make_dantzig, "late": make_late}[w]()

@@ -303,3 +303,63 @@ def test_dantzig_rule_equals_reference_driven_by_column_swap(reference_module):
         o = oracle.solve(rows, c, max_pivots=150, rule="dantzig")
         assert o.status == END_TO_STATUS[end] and o.trace.tolist() == trace, t
         assert table_sha(o.table) == mg.table_sha(sm.table), t
+
+
+# --------------------------------------------------------------------------- fixtures bench.py asserts at run time
+def test_body_checksum_is_shardable_and_layout_free():
+    """workloads.body_checksum_*: numpy (golden side) == torch (device side), strided views, and the column
+    shards' checksums add up mod 2^64 to the whole body's."""
+    import torch
+    rng = np.random.default_rng(5)
+    n, m = 70, 333
+    big = np.zeros((n + 1, 400))
+    big[:, :m] = rng.standard_normal((n + 1, m))
+    body = big[:n, :m]
+    whole = W.body_checksum_numpy(body)
+    bits_ = np.ascontiguousarray(body).view(np.uint64)
+    ref = sum(int(bits_[i, j]) * (2 * (i * m + j) + 1) for i in range(n) for j in range(m)) % (1 << 64)
+    assert whole == ref
+    t = torch.from_numpy(big)
+    assert W.body_checksum_torch(t[:n, :m]) == whole
+    parts = [W.body_checksum_torch(t[:n, a:b], m_total=m, col0=a) for a, b in ((0, 100), (100, 101), (101, 333))]
+    assert sum(parts) % (1 << 64) == whole
+    body2 = body.copy()
+    body2[3, 7] = np.nextafter(body2[3, 7], 1.0)
+    assert W.body_checksum_numpy(body2) != whole
+
+
+def test_late_lp_golden_of_the_multi_gpu_preflight():
+    """tests/golden/late_lp.json (asserted by bench.py at N > 1 before anything is timed) == the oracle today."""
+    import json
+    import os
+    from util import make_lp
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "late_lp.json")) as fh:
+        g = json.load(fh)
+    rows, c = make_lp(g["n"], g["m"], g["seed"], "late")
+    assert W.input_digest(rows, c) == g["input_sha256"]
+    o = oracle.solve(rows, c, max_pivots=100000)
+    n, m = g["n"], g["m"]
+    body = o.table[: n * (m + 1)].reshape(n, m + 1)
+    assert (o.status, o.npiv) == (g["status"], g["npiv"]) and o.trace.tolist() == g["trace"]
+    assert hashlib.sha256(np.ascontiguousarray(body[:, m]).tobytes()).hexdigest() == g["b_sha256"]
+    assert hashlib.sha256(o.table[n * (m + 1):].tobytes()).hexdigest() == g["f_sha256"]
+    assert W.body_checksum_numpy(body[:, :m]) == g["body_checksum_u64"]
+    assert min(g["owner_changes"].values()) >= 100
+
+
+def test_cfg4_long_golden_extends_the_2000_pivot_golden(cfg_digests):
+    """tests/golden/cfg4_long.json (every timed pivot of bench.py) starts with the round-1 golden, mark for mark."""
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(here, "cfg4_long.json")) as fh:
+        gl = json.load(fh)
+    tr = np.load(os.path.join(here, "cfg4_long_trace.npy"))
+    old = cfg_digests["cfg4"]
+    assert gl["input_sha256"] == old["input_sha256"] and gl["provenance"] == "oracle"
+    assert tr[:2000].tolist() == old["trace"] and gl["npiv"] == len(tr) >= 25000
+    for k, mk in old["marks"].items():
+        for field in ("pivot_sha256", "b_sha256", "f_sha256"):
+            assert gl["marks"][k][field] == mk[field], (k, field)
+    for k, mk in gl["marks"].items():
+        assert W.pivot_digest(tr[: int(k)]) == mk["pivot_sha256"], k
