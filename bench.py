@@ -624,6 +624,10 @@ def run_ours(args):
         # a rank that fails an assertion must not leave its peers in a collective for NCCL's default 10 minutes
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     N.lib()
+    if args.shard_threads:
+        assert N.load().spx_set_option(13, args.shard_threads) == 0
+    if args.shard_ctas:
+        assert N.load().spx_set_option(14, args.shard_ctas) == 0
     peak, peak_src = measured_peak()
     in_sha, gold, marks = golden_cfg4()
 
@@ -813,7 +817,7 @@ def run_ours(args):
         sh, err = None, ""
         try:
             sh = FusedShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
-                                     depth=args.depth or fused_depth_for(world))
+                                     depth=args.depth or fused_depth_for(world), lookahead=not args.no_lookahead)
         except Exception as e:                       # noqa: BLE001 - reported below, then the documented fallback
             err = f"{type(e).__name__}: {e}"
         okf = torch.tensor([1 if sh is not None else 0], dtype=torch.int32, device=dev)
@@ -898,6 +902,19 @@ def run_ours(args):
         return (hashlib.sha256(bcur.cpu().numpy().tobytes()).hexdigest(), hashlib.sha256(b"".join(fs)).hexdigest(),
                 int(ck.item()) & 0xFFFFFFFFFFFFFFFF)
 
+    pricing_levels = None
+    if args.exchange == "fused" and rank == 0:
+        # per-level phase breakdown of the LAST pricing kernel of the timed region (%globaltimer stamps, rank 0)
+        stp = sh.pricing_stamps().astype(np.int64)
+        dep = args.depth or fused_depth_for(world)
+        lv = stp[1:dep]                                  # levels 1..depth-1 of the pass: all six stamps are from this launch
+        d = np.diff(np.concatenate([stp[0:dep - 1, 5:6], lv], axis=1), axis=1) / 1e3
+        pricing_levels = {"us_per_level": float((stp[dep - 1, 5] - stp[0, 5]) / ((dep - 1) * 1e3)),
+                          "phases_us_mean": {k: float(v) for k, v in zip(
+                              ["phase_A_b_f_row_replay", "grid_barrier_entering_column", "candidate_column_build_and_store",
+                               "arrive_nvlink_key_exchange_broadcast", "ratio_fold_grid_barrier", "final_merge_and_record"],
+                              d.mean(axis=0))},
+                          "how": f"%globaltimer stamps by thread 0 of rank 0 in shard_price_kernel, last pass, levels 1-{dep - 1}"}
     parity = "sharded " + check_against_marks(tr, need, marks, gold, table_digests)
     value = args.steps * P / (total_ms * 1e-3)
     alg_bytes = 16.0 * cells(N_ROWS, M_COLS)
@@ -955,6 +972,7 @@ def run_ours(args):
                          "frac": alg_bytes * args.steps * P / (total_ms * 1e-3) / 1e9 / world / peak,
                          "traffic": None},
             "cpu_baseline": None, "batched": batched, "batched_1M": batched_big,
+            "pricing_level_breakdown": pricing_levels,
             "parity": parity,
             "parity_owner_changes": owner_changes,
             "parity_late_lp": (None if owner_changes is None else
@@ -981,6 +999,10 @@ def main():
     ap.add_argument("--exchange", default="fused", choices=["fused", "p2p", "nccl"],
                     help="N>1: fused passes with the in-kernel NVLink exchange (default); pivot-at-a-time look-ahead "
                          "with NVLink peer mailboxes (p2p) or an NCCL all-gather (nccl)")
+    ap.add_argument("--shard-threads", type=int, default=0,
+                    help="N>1 fused loop: threads per CTA of the sharded pricing kernel (0 = library default)")
+    ap.add_argument("--shard-ctas", type=int, default=0,
+                    help="N>1 fused loop: cap on the CTAs (= SMs) of the sharded pricing kernel (0 = library default)")
     ap.add_argument("--no-lookahead", action="store_true",
                     help="classic pick->update order instead of pricing pivot k+1 during update k")
     args = ap.parse_args()

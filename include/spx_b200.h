@@ -103,6 +103,8 @@ int64_t     spx_launch_count(int reset);
 #define SPX_OPT_FUSE_LOOKAHEAD   9  /* fused loop in spx_solve: 1 = price pass q+1 on a side stream during update q (default 0: off on one GPU) */
 #define SPX_OPT_FUSE_VARIANT     10 /* fused update kernel: 0 default (lazy range guard: one range test per cell per PASS), 1 = round 1's kernel (range test per cell per level) */
 #define SPX_OPT_FUSE_TILE_ROWS   11 /* fused update kernel: rows of the strip one warp walks (0 = 128; a multiple of 8 <= 4096) */
+#define SPX_OPT_SHARD_THREADS    13 /* sharded / look-ahead pricing kernel: threads per CTA, one CTA per SM (0 = default 512; 64..512, multiple of 32) */
+#define SPX_OPT_SHARD_CTAS       14 /* sharded / look-ahead pricing kernel: at most this many CTAs (0 = one per SM) */
 #define SPX_OPT_FUSE_PAIRS       12 /* fused update kernel: column pairs per lane, i.e. strip width / 64 (0 = default 2; 1 or 2) */
 int         spx_set_option(int32_t option, int64_t value);
 int64_t     spx_get_option(int32_t option);
@@ -330,6 +332,11 @@ int spx_fshard_set_lookahead(spx_fshard *h, int32_t on);
 int spx_fshard_enqueue(spx_fshard *h, int64_t pivots, int32_t depth, void *stream);
 int spx_fshard_read(spx_fshard *h, spx_state *h_state, int32_t *cur_buffer, void *stream);
 int spx_fshard_close(spx_fshard *h);
+/* Developer aid: the %globaltimer stamps (ns) the sharded pricing kernel left in the fused workspace `d_work` during
+ * its LAST launch: h_out[9][6] = per level {phase A done, entering column known (grid barrier 1), candidate columns
+ * stored on every rank, keys exchanged over NVLink, ratio partials in (grid barrier 2), level recorded}.
+ * Synchronises `stream`.  No reference counterpart. */
+int spx_fused_debug_stamps(const void *d_work, int32_t n, int64_t ld, uint64_t *h_out, int32_t capacity, void *stream);
 
 #ifdef __cplusplus
 }

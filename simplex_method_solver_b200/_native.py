@@ -111,6 +111,7 @@ SIGNATURES = {
     "spx_fshard_enqueue": (ctypes.c_int, [_vp, _i64, _i32, _vp]),
     "spx_fshard_read": (ctypes.c_int, [_vp, _vp, _pi32, _vp]),
     "spx_fshard_close": (ctypes.c_int, [_vp]),
+    "spx_fused_debug_stamps": (ctypes.c_int, [_vp, _i32, _i64, ctypes.POINTER(ctypes.c_uint64), _i32, _vp]),
 }
 
 _lib = None

@@ -215,10 +215,15 @@ block_price_kernel(PriceArgs a) {
 // entering column (an index min) and the leaving row (the ratio fold) — go through global scratch and
 // a grid barrier: two barriers per level, ~10 us per level.  Data written by other CTAs during the
 // kernel is read with ld.global.cg (L1 is not coherent across SMs).
+constexpr int STAMPS = 6;                       // shard_price_kernel: %globaltimer per level at its phase boundaries
 struct CoopScratch {
     int   idx[FUSE_MAX + 1][4];                 // per level: [first negative b, entering column, phase-1 column, -]
     unsigned long long key[FUSE_MAX + 1];       // Dantzig: most negative running f value (orderable image)
-};
+    unsigned int       arrive;                  // shard_price_kernel: CTAs whose candidate-column stores are fenced
+    unsigned int       pad;
+    unsigned long long bcast;                   // ... and the epoch of the last exchange result CTA 0 published
+    unsigned long long stamp[FUSE_MAX + 1][STAMPS];   // debug: ns at level start / after sync 1 / column stored / keys
+};                                              //        exchanged / ratio partials synced / level done (thread 0)
 
 struct CoopArgs {
     PriceArgs  a;
@@ -458,6 +463,36 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// Lazy replay of up to 2 * FUSE_MAX pending levels on ONE cell with every level's global operand in flight at once:
+// `op[l] = ptr[l][idx]` does not depend on the running value, but a rolled loop issues load l + 1 only after
+// apply_level(l) has consumed load l — up to 15 serialised L2 round trips per cell on the critical path of a level.
+// ROWOP: the loaded operand is the level's ROW value (the scalar its COL value), or the other way round.
+template <bool ROWOP>
+__device__ __forceinline__ double replay_levels(double v, int t, int j, int nl, const LevelDiv *lvl,
+                                                const double *const *ptr, int64_t idx, const double *scal) {
+    double op[2 * FUSE_MAX];
+#pragma unroll
+    for (int l = 0; l < 2 * FUSE_MAX; ++l) op[l] = (l < nl) ? __ldcg(ptr[l] + idx) : 0.0;
+#pragma unroll
+    for (int l = 0; l < 2 * FUSE_MAX; ++l)
+        if (l < nl) v = ROWOP ? apply_level(v, t, j, lvl[l], op[l], scal[l]) : apply_level(v, t, j, lvl[l], scal[l], op[l]);
+    return v;
+}
+
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // spin until *flag >= seq; false after 20 s (a peer died)
 __device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigned long long seq) {
     const unsigned long long t0 = gtimer_ns();
@@ -595,9 +630,7 @@ shard_price_kernel(ShardArgs sa) {
             const double *rowp = A + (int64_t)L.r * ld;
             for (int j = gtid; j < ld; j += gn) {
                 if (j >= m) { ROWL[j] = 0.0; continue; }
-                double rv = rowp[j];
-                for (int l = 0; l < np + i - 1; ++l)
-                    rv = apply_level(rv, L.r, j, s_lvl[l], __ldcg(s_rowp[l] + j), s_scal[l]);
+                const double rv = replay_levels<true>(rowp[j], L.r, j, np + i - 1, s_lvl, s_rowp, j, s_scal);
                 ROWL[j] = rv;
                 const double fj = a.frow[j];
                 const double v = (j == L.c) ? pivot_div(fc, L.d) : cell_update(fj, L.d, rv, fc);
@@ -606,6 +639,7 @@ shard_price_kernel(ShardArgs sa) {
             }
         }
         if (i == a.F) { f = a.F; break; }
+        if (gtid == 0) ca.cs->stamp[i][0] = gtimer_ns();
         bneg = block_min_int(bneg, s);
         fneg = block_min_int(fneg, s);
         if (tid == 0) {
@@ -617,6 +651,7 @@ shard_price_kernel(ShardArgs sa) {
             if (tid == 0 && fkey != ~0ull) atomicMin(&ca.cs->key[i], fkey);
         }
         grid.sync();
+        if (gtid == 0) ca.cs->stamp[i][1] = gtimer_ns();
         const int rb = __ldcg(&ca.cs->idx[i][0]);
         const int r1 = (rb == SPX_NONE) ? -1 : rb;       // identical on every rank: b is replicated
         int cloc = __ldcg(&ca.cs->idx[i][1]);            // this rank's candidate (local index)
@@ -630,8 +665,7 @@ shard_price_kernel(ShardArgs sa) {
             const double *row = A + (int64_t)r1 * ld;
             int loc = SPX_NONE;
             for (int j = gtid; j < m; j += gn) {
-                double v = row[j];
-                for (int l = 0; l < np + i; ++l) v = apply_level(v, r1, j, s_lvl[l], __ldcg(s_rowp[l] + j), s_scal[l]);
+                const double v = replay_levels<true>(row[j], r1, j, np + i, s_lvl, s_rowp, j, s_scal);
                 if (v > 0.0) { loc = j; break; }
             }
             loc = block_min_int(loc, s);
@@ -658,19 +692,39 @@ shard_price_kernel(ShardArgs sa) {
             __syncthreads();
             const int64_t plane = (((int64_t)par * FUSE_MAX + i) * sa.R + sa.rank) * cbd;
             for (int t = gtid; t <= n; t += gn) {
-                double w = A[(int64_t)t * ld + cloc];
-                for (int l = 0; l < np + i; ++l) w = apply_level(w, t, cloc, s_lvl[l], s_scal[l], __ldcg(s_colp[l] + t));
+                const double w = replay_levels<false>(A[(int64_t)t * ld + cloc], t, cloc, np + i, s_lvl, s_colp, t, s_scal);
                 for (int g = 0; g < sa.R; ++g)
                     (reinterpret_cast<double *>(sa.xbox[g] + XL.cols_off) + plane)[t] = w;
             }
         }
-        __threadfence_system();
-        grid.sync();
-        // ---------------- one exchange: key + flag (the column stores above are ordered before the flag)
-        if (blockIdx.x == 0)
-            exchange_keys(sa, XL, kpar, i, kind, (cloc == SPX_NONE) ? ~0ull : kh,
-                          (cloc == SPX_NONE) ? ~0ull : (unsigned long long)(col0 + cloc), gsel);
-        grid.sync();
+        // ---------------- one exchange: key + flag.  Instead of two grid barriers around it: every CTA fences its
+        // column stores and ARRIVES at a counter; CTA 0 waits for all of them (the stores are then ordered before
+        // the flag it releases to the peers), exchanges, and BROADCASTS the result under a per-level epoch the
+        // other CTAs spin on — an all-to-one plus a one-to-all instead of two all-to-alls.
+        {
+            const unsigned long long epoch = sa.seq * (unsigned long long)(2 * FUSE_MAX) + (unsigned long long)i + 1ull;
+            __threadfence_system();
+            __syncthreads();
+            if (blockIdx.x == 0) {
+                if (tid == 0) {
+                    atomicAdd(&ca.cs->arrive, 1u);
+                    while (ld_acquire_gpu_u32(&ca.cs->arrive) < (unsigned)G) { }
+                    ca.cs->arrive = 0u;                      // nobody arrives again before the broadcast below
+                    ca.cs->stamp[i][2] = gtimer_ns();
+                }
+                __syncthreads();
+                exchange_keys(sa, XL, kpar, i, kind, (cloc == SPX_NONE) ? ~0ull : kh,
+                              (cloc == SPX_NONE) ? ~0ull : (unsigned long long)(col0 + cloc), gsel);
+                __syncthreads();
+                if (tid == 0) { __threadfence(); st_release_gpu_u64(&ca.cs->bcast, epoch); }
+            } else if (tid == 0) {
+                __threadfence();
+                atomicAdd(&ca.cs->arrive, 1u);
+                while (ld_acquire_gpu_u64(&ca.cs->bcast) != epoch) { }
+            }
+            __syncthreads();
+        }
+        if (gtid == 0) ca.cs->stamp[i][3] = gtimer_ns();
         const int c = __ldcg(gsel + 0), owner = __ldcg(gsel + 1);
         if (__ldcg(gsel + 2)) { status = SPX_PEER_TIMEOUT; f = i; break; }
         if (c == SPX_NONE) { status = (r1 >= 0) ? SPX_INCORRECT : SPX_OPTIMAL; phase1 = (r1 >= 0); f = i; break; }
@@ -691,6 +745,7 @@ shard_price_kernel(ShardArgs sa) {
         Ratio *part = ca.part + (int64_t)i * G;
         if (tid == 0) part[blockIdx.x] = q;
         grid.sync();
+        if (gtid == 0) ca.cs->stamp[i][4] = gtimer_ns();
         int r;
         if (r1 >= 0) {
             r = r1;
@@ -717,6 +772,7 @@ shard_price_kernel(ShardArgs sa) {
         if (tid == 0) {
             s_lvl[np + i].r = r; s_lvl[np + i].c = clocal; s_lvl[np + i].d = pivot_div_prepare(p);
             if (blockIdx.x == 0) {
+                ca.cs->stamp[i][5] = gtimer_ns();
                 a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p;       // GLOBAL column in the plan
                 a.plan->owner[i] = owner;
                 const int32_t tmp = a.rowlab[c]; a.rowlab[c] = a.collab[r]; a.collab[r] = tmp;
@@ -1443,10 +1499,18 @@ static cudaError_t launch_shard_price(const FusedCtx &c, const FusedWork &w, int
             g_shard_ctas = min(COOP_MAX_CTAS, sm_count());
     }
     if (g_shard_ctas <= 0) return cudaErrorNotSupported;
-    int G = (max(c.n + 1, (int)c.ld) + COOP_THREADS - 1) / COOP_THREADS;
-    G = G > g_shard_ctas ? g_shard_ctas : (G < 1 ? 1 : G);
+    // threads per CTA (one CTA per SM).  Measured at N = 8 (profiles/r2/): 128 / 256 / 384 / 512 threads ->
+    // 13.5 / 17.6 / 19.0 / 18.7 k pivots/s.
+    int threads = (int)get_option(SPX_OPT_SHARD_THREADS);
+    if (threads <= 0) threads = 512;
+    int G = (max(c.n + 1, (int)c.ld) + threads - 1) / threads;
+    // SPX_OPT_SHARD_CTAS caps the grid (one CTA per SM): the SMs the pricing kernel does NOT occupy keep streaming
+    // the update of the previous pass while it runs
+    const int cap_ctas = (int)get_option(SPX_OPT_SHARD_CTAS);
+    const int max_ctas = (cap_ctas > 0 && cap_ctas < g_shard_ctas) ? cap_ctas : g_shard_ctas;
+    G = G > max_ctas ? max_ctas : (G < 1 ? 1 : G);
     void *args[] = {&sa};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)shard_price_kernel, dim3(G), dim3(COOP_THREADS), args, 0, stream);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)shard_price_kernel, dim3(G), dim3(threads), args, 0, stream);
     if (e == cudaSuccess) spx_host::count_launch();
     return e;
 }
@@ -1544,6 +1608,15 @@ cudaError_t fused_solo_sync() {
     return cudaSuccess;
 }
 
+// debug: the %globaltimer stamps of the LAST shard_price_kernel launch on this workspace, [FUSE_MAX + 1][STAMPS]
+cudaError_t fused_debug_stamps(const void *work, int n, int64_t ld, unsigned long long *h_out, cudaStream_t s) {
+    const FusedWork w = carve_work(const_cast<void *>(work), n, ld);
+    cudaError_t e = cudaMemcpyAsync(h_out, w.cs->stamp, sizeof(w.cs->stamp), cudaMemcpyDeviceToHost, s);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(s);
+}
+int fused_debug_stamp_count() { return (FUSE_MAX + 1) * STAMPS; }
+
 int64_t xbox_bytes(int n, int R) { return xbox_layout(colbuf_doubles(n), R).bytes; }
 int xbox_max_ranks() { return XB_MAX_RANKS; }
 
@@ -1617,6 +1690,15 @@ int spx_fshard_read(spx_fshard *h, spx_state *h_state, int32_t *cur_buffer, void
     if (spx_host::check(cudaStreamSynchronize(s), "sync")) return -1;
     if (cur_buffer) *cur_buffer = (int32_t)(h_state->reserved[0] & 1);
     return 0;
+}
+
+int spx_fused_debug_stamps(const void *d_work, int32_t n, int64_t ld, uint64_t *h_out, int32_t capacity, void *stream) {
+    if (!d_work || !h_out || n < 1 || ld < 16 || capacity < spx_launch::fused_debug_stamp_count()) {
+        spx_host::set_error("spx_fused_debug_stamps: bad arguments");
+        return -2;
+    }
+    return spx_host::check(spx_launch::fused_debug_stamps(d_work, n, ld, reinterpret_cast<unsigned long long *>(h_out),
+                                                          reinterpret_cast<cudaStream_t>(stream)), "debug stamps");
 }
 
 int spx_fshard_close(spx_fshard *h) {

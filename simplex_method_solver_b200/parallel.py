@@ -513,6 +513,14 @@ class FusedShardedTableau(ShardedTableau):
         self.read_state()
         return self.b[self._cur, : self.n]
 
+    def pricing_stamps(self) -> np.ndarray:
+        """[9, 6] uint64 ns: the phase stamps of the last pricing kernel on this rank (spx_fused_debug_stamps)."""
+        out = (ctypes.c_uint64 * 54)()
+        with torch.cuda.device(self.device):
+            N.call("spx_fused_debug_stamps", self.work.data_ptr(), self.n, self.ld, out, 54,
+                   torch.cuda.current_stream(self.device).cuda_stream)
+        return np.frombuffer(out, dtype=np.uint64).reshape(9, 6).copy()
+
     def close(self):
         if self.handle:
             N.call("spx_fshard_close", self.handle)
