@@ -236,6 +236,10 @@ def python_reference_timings(budget_s=2.0):
         k1, _ = drive(W.CFG1_ROWS, W.CFG1_C)
     dt = (time.perf_counter() - t0) / reps
     out["cfg1"] = {"pivots": k1, "solves_per_s": 1.0 / dt, "pivots_per_s": k1 / dt, "sample": f"{reps} full solves"}
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ref.SimplexMethod([list(map(float, r)) for r in W.CFG1_ROWS], [float(v) for v in W.CFG1_C]).get_solution()
+    out["cfg1"]["get_solution_per_s"] = reps / (time.perf_counter() - t0)     # what the GUI calls (snapshots included)
     T, C = W.gui_batch(4096, 0)
     t0 = time.perf_counter()
     piv = sum(drive(T[k], C[k])[0] for k in range(4096))

@@ -253,7 +253,8 @@ cudaError_t solve_batched(double *T, int64_t B, int n, int m, int rule, int max_
     if (lb + wb > SMEM_LIMIT) return cudaErrorInvalidValue;
     const int64_t cells = (int64_t)n * (m + 1) + m;
     BatchedArgs a{T, B, n, m, rule, max_pivots, x, obj, status, npiv, rowlab, collab, trace, snap};
-    static size_t configured[2] = {0, 0};
+    static size_t configured_dev[64][2] = {};
+    size_t *configured = configured_dev[spx_host::device_slot()];
     if (cells > CTA_MODE_MIN_CELLS) {
         // one CTA per LP: one cell per thread where possible (measured on Klee-Minty n=20: 32 cells per warp
         // 891 k pivots/s, 64: 730 k, 128: 623 k), 2..16 warps

@@ -1423,7 +1423,8 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
     if (phase == 1) return cudaSuccess;
     if ((e = launch_update_variant(A0, A1, n, m, ld, cbd, col0, 1, plan, ROWS, COLS, minb, true, stream)) != cudaErrorNotSupported)
         return e;
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    bool &configured = configured_dev[spx_host::device_slot()];
     if (!configured) {
         if ((e = cudaFuncSetAttribute(update_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(update_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
@@ -1518,7 +1519,8 @@ static cudaError_t launch_shard_price(const FusedCtx &c, const FusedWork &w, int
 static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, int h, int minb, bool persistent,
                                        cudaStream_t stream) {
     const int slot3 = (int)(c.seq % 3ull);               // the COL planes of this pass (c.seq = its pass number)
-    static bool configured = false;
+    static bool configured_dev[64] = {};
+    bool &configured = configured_dev[spx_host::device_slot()];
     cudaError_t e;
     if (!configured) {
         if ((e = cudaFuncSetAttribute(update_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;

@@ -229,6 +229,12 @@ bool resident_fits(int n, int m, int64_t ld) {
                 g_res_grid = per_sm * sm_count();
         }
     }
+    static bool attr_dev[64] = {};                           // the dynamic shared-memory limit is a per-device attribute
+    bool &attr = attr_dev[spx_host::device_slot()];
+    if (g_res_grid > 0 && !attr) {
+        cudaFuncSetAttribute(resident_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resident_smem(RES_MAX_N));
+        attr = true;
+    }
     return g_res_grid > 0;
 }
 

@@ -461,7 +461,8 @@ cudaError_t update(const double *Ain, double *Aout, const double *bin, double *b
     // pipelined kernel stays selectable for experiments
     if (kernel == 0) kernel = 1;
     if (kernel == 2) {
-        static bool configured = false;
+        static bool configured_dev[64] = {};
+        bool &configured = configured_dev[spx_host::device_slot()];
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(update_pipelined_kernel,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM);
