@@ -176,7 +176,7 @@ def config_dict():
             "rule": "reference (first-negative entering, max-negative-ratio leaving)"}
 
 
-def implementation_dict(ngpu, exchange="fused", fallback=None):
+def implementation_dict(ngpu, exchange="fused", fallback=None, price_engine=None):
     d = {"loop": "fused: 8 pivots priced from the stored table (coop_price_kernel), then ONE stream over the body applies "
                  "them (update_lazy_kernel, csrc/spx_fused.cu)" if ngpu == 1 else
                  "fused, column-sharded: cooperative pricing with the in-kernel NVLink exchange of keys and the pivot "
@@ -188,6 +188,14 @@ def implementation_dict(ngpu, exchange="fused", fallback=None):
         d["exchange"] = exchange
     if fallback:
         d["exchange_fallback"] = fallback
+    if os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"):
+        d["cuda_device_max_connections"] = os.environ["CUDA_DEVICE_MAX_CONNECTIONS"]
+    if price_engine:
+        d["price_engine"] = price_engine + (
+            ": ONE cooperative pricing kernel per run() call stays resident and hands passes to the update kernels "
+            "through device flags" if price_engine == "persistent" else
+            ": one cooperative pricing kernel per pass on a high-priority side stream, events between it and the "
+            "update kernels" if price_engine == "per-pass" else "")
     return d
 
 
@@ -814,32 +822,43 @@ def run_ours(args):
     from simplex_method_solver_b200.parallel import FusedShardedTableau, PeerShardedTableau, ShardedTableau
     fallback_note = None
     owner_changes = None
+    price_engine = None
     if args.exchange == "fused":
         # passes of 8 pivots: cooperative pricing with the in-kernel NVLink exchange, then ONE stream
         # over the local columns applies them all (csrc/spx_fused.cu).  If peer memory cannot be mapped on
         # this box (no CUDA IPC / P2P between the GPUs) every rank falls back to the NCCL all-gather flow.
-        sh, err = None, ""
-        try:
-            sh = FusedShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
-                                     depth=args.depth or fused_depth_for(world), lookahead=not args.no_lookahead)
-        except Exception as e:                       # noqa: BLE001 - reported below, then the documented fallback
-            err = f"{type(e).__name__}: {e}"
-        okf = torch.tensor([1 if sh is not None else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
-        if int(okf.item()) == 0:
-            log(f"[rank {rank}] peer-memory exchange unavailable ({err or 'a peer failed'}); falling back to --exchange nccl")
-            fallback_note = f"peer memory unavailable ({err or 'on a peer'})"
-            if sh is not None:
-                sh.close()
-            args.exchange = "nccl"
-            sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
-                                lookahead=not args.no_lookahead)
+        # Pricing engines to try, in order: the persistent engine (one pricing kernel per run() call, device-flag
+        # hand-shakes with the update kernels — the default from 8 ranks on) and the per-pass engine (one pricing
+        # kernel per pass).  Each goes through the same two preflights before it may be timed.
+        if args.no_lookahead:
+            engines = [False]
+        elif args.price_engine == "auto":
+            engines = ["persistent", "per-pass"] if world >= FusedShardedTableau.PERSISTENT_FROM_WORLD else ["per-pass"]
         else:
+            engines = [args.price_engine] + (["per-pass"] if args.price_engine == "persistent" else [])
+        sh, peer_memory_ok, notes = None, True, []
+        for engine in engines:
+            sh, err = None, ""
+            try:
+                sh = FusedShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
+                                         depth=args.depth or fused_depth_for(world), lookahead=engine)
+            except Exception as e:                   # noqa: BLE001 - reported below, then the documented fallback
+                err = f"{type(e).__name__}: {e}"
+            okf = torch.tensor([1 if sh is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if int(okf.item()) == 0:
+                log(f"[rank {rank}] peer-memory exchange unavailable ({err or 'a peer failed'}); falling back to --exchange nccl")
+                notes.append(f"peer memory unavailable ({err or 'on a peer'})")
+                if sh is not None:
+                    sh.close()
+                sh, peer_memory_ok = None, False
+                break
             # preflight 1: the committed "late" LP — entering columns owned by every rank, > 100 owner changes —
             # full table against the oracle's golden; preflight 2: a few passes of cfg4 against the golden prefix.
-            # A rank that times out on a peer (SPX_PEER_TIMEOUT) or diverges sends all ranks to the pivot-at-a-time
-            # peer-mailbox loop instead (csrc/spx_shard.cu), and the printed line says so
-            ok_late, owner_changes, why = late_lp_preflight(FusedShardedTableau, rank, world, dev, dist)
+            # A rank that times out on a peer (SPX_PEER_TIMEOUT) or diverges sends all ranks to the next engine and,
+            # after the last one, to the pivot-at-a-time peer-mailbox loop (csrc/spx_shard.cu); the printed line says so
+            ok_late, owner_changes, why = late_lp_preflight(
+                lambda *a_, **k_: FusedShardedTableau(*a_, lookahead=engine, **k_), rank, world, dev, dist)
             pre = 96
             if ok_late:
                 try:
@@ -855,12 +874,22 @@ def run_ours(args):
                     why = f"{type(e).__name__}: {e}"
             okf = torch.tensor([0 if why else 1], dtype=torch.int32, device=dev)
             dist.all_reduce(okf, op=dist.ReduceOp.MIN)
-            if int(okf.item()) == 0:
-                log(f"[rank {rank}] fused exchange failed its preflight ({why or 'on a peer'}); falling back to --exchange p2p")
-                fallback_note = f"fused preflight failed ({why or 'on a peer'})"
-                sh.close()
-                args.exchange = "p2p"
-                sh = PeerShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
+            if int(okf.item()) == 1:
+                price_engine = {False: "none (no look-ahead)"}.get(engine, engine)
+                break
+            log(f"[rank {rank}] fused exchange, pricing engine {engine!r}, failed its preflight ({why or 'on a peer'})")
+            notes.append(f"fused preflight failed with pricing engine {engine!r} ({why or 'on a peer'})")
+            sh.close()
+            sh = None
+        if sh is None and not peer_memory_ok:
+            args.exchange = "nccl"
+            sh = ShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64,
+                                lookahead=not args.no_lookahead)
+        elif sh is None:
+            log(f"[rank {rank}] falling back to --exchange p2p")
+            args.exchange = "p2p"
+            sh = PeerShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
+        fallback_note = "; ".join(notes) or None
     elif args.exchange == "p2p":
         # C-side look-ahead loop, candidates exchanged by NVLink peer stores (csrc/spx_shard.cu)
         sh = PeerShardedTableau(N_ROWS, M_COLS, rank, world, device=dev, trace_capacity=need + 64)
@@ -965,7 +994,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(), "implementation": implementation_dict(world, args.exchange, fallback_note),
+            "config": config_dict(),
+            "implementation": implementation_dict(world, args.exchange, fallback_note,
+                                                  price_engine if args.exchange == "fused" else None),
             "clocks": clk.summary(),
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm",
@@ -982,7 +1013,7 @@ def run_ours(args):
             "parity_late_lp": (None if owner_changes is None else
                                f"late LP (tests/golden/late_lp.json) through the fused sharded loop on {world} ranks: trace, b, "
                                f"f and body checksum == oracle golden; the entering column changed owner rank {owner_changes} times"
-                               if not (fallback_note or "").startswith("fused preflight") else "FAILED: " + fallback_note),
+                               if args.exchange == "fused" else "FAILED: " + str(fallback_note)),
         }
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
@@ -1007,9 +1038,16 @@ def main():
                     help="N>1 fused loop: threads per CTA of the sharded pricing kernel (0 = library default)")
     ap.add_argument("--shard-ctas", type=int, default=0,
                     help="N>1 fused loop: cap on the CTAs (= SMs) of the sharded pricing kernel (0 = library default)")
+    ap.add_argument("--price-engine", default="auto", choices=["auto", "persistent", "per-pass"],
+                    help="N>1 fused loop: pricing engine (auto = persistent from 8 ranks on, else one kernel per pass)")
     ap.add_argument("--no-lookahead", action="store_true",
                     help="classic pick->update order instead of pricing pivot k+1 during update k")
+    ap.add_argument("--max-connections", type=int, default=0,
+                    help="CUDA_DEVICE_MAX_CONNECTIONS for this process (hardware work queues the streams share; the CUDA "
+                         "default is 8); 0 = leave the environment alone.  Must be set before CUDA initialises.")
     args = ap.parse_args()
+    if args.max_connections > 0:
+        os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] = str(args.max_connections)
     if args.warmup < 3 and args.impl == "ours":
         log("note: the timing rules ask for >= 3 warm-up steps")
     if args.impl == "reference":

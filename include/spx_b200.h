@@ -100,11 +100,12 @@ int64_t     spx_launch_count(int reset);
 #define SPX_OPT_FUSE_DEPTH       6  /* fused loop: pivots applied per pass over the body (0 = default 8, max 8) */
 #define SPX_OPT_FUSE_MIN_BLOCKS  7  /* fused update kernel: resident CTAs per SM its register budget targets (2..4, 0 = default 3) */
 #define SPX_OPT_FUSE_PRICING     8  /* fused loop pricing kernel: 0 auto, 1 one CTA, 2 whole-GPU cooperative */
-#define SPX_OPT_FUSE_LOOKAHEAD   9  /* fused loop in spx_solve: 1 = price pass q+1 on a side stream during update q (default 0: off on one GPU) */
+#define SPX_OPT_FUSE_LOOKAHEAD   9  /* fused loop in spx_solve: 1 = price pass q+1 on a side stream during update q, 2 = the same with the persistent pricing engine (see spx_fshard_set_lookahead); default 0: off on one GPU */
 #define SPX_OPT_FUSE_VARIANT     10 /* fused update kernel: 0 default (lazy range guard: one range test per cell per PASS), 1 = round 1's kernel (range test per cell per level) */
 #define SPX_OPT_FUSE_TILE_ROWS   11 /* fused update kernel: rows of the strip one warp walks (0 = 128; a multiple of 8 <= 4096) */
 #define SPX_OPT_SHARD_THREADS    13 /* sharded / look-ahead pricing kernel: threads per CTA, one CTA per SM (0 = default 512; 64..512, multiple of 32) */
 #define SPX_OPT_SHARD_CTAS       14 /* sharded / look-ahead pricing kernel: at most this many CTAs (0 = one per SM) */
+#define SPX_OPT_RESIDENT_VARIANT 15 /* L2-resident persistent loop: 0 default (price, sweep, one grid barrier per pivot), 1 = look-ahead pricing inside the CTA with the sweep rows prefetched by cp.async (bit-identical; measured slower on cfg2, kept selectable) */
 #define SPX_OPT_FUSE_PAIRS       12 /* fused update kernel: column pairs per lane, i.e. strip width / 64 (0 = default 2; 1 or 2) */
 int         spx_set_option(int32_t option, int64_t value);
 int64_t     spx_get_option(int32_t option);
@@ -326,8 +327,12 @@ int spx_fshard_open(spx_fshard **out, int32_t rank, int32_t nranks, int32_t n, i
                     int64_t col0, int32_t rule, double *d_A0, double *d_A1, double *d_b0, double *d_b1,
                     spx_state *d_state, void *d_work, int64_t work_bytes, int32_t *d_rowlab, int32_t *d_collab,
                     int32_t *d_trace, void *const *xboxes);
-/* look-ahead (default on): the pricing of pass q+1 runs on the handle's high-priority side stream while
- * the update of pass q streams; off: price, update, price, ... on `stream`. */
+/* look-ahead (default 1): the pricing of pass q+1 runs on the handle's high-priority side stream while
+ * the update of pass q streams; 0: price, update, price, ... on `stream`; 2: look-ahead with a PERSISTENT
+ * pricing engine — one cooperative pricing kernel per spx_fshard_enqueue call prices every pass and keeps its
+ * SMs, the update kernels of all passes are enqueued behind it at once, and the two dependencies (update q
+ * needs plan q; pricing q needs the table of update q-2) go through device flags instead of one cooperative
+ * launch and two events per pass.  For pricing-bound shards (8 ranks on cfg4).  Every rank must use the same mode. */
 int spx_fshard_set_lookahead(spx_fshard *h, int32_t on);
 int spx_fshard_enqueue(spx_fshard *h, int64_t pivots, int32_t depth, void *stream);
 int spx_fshard_read(spx_fshard *h, spx_state *h_state, int32_t *cur_buffer, void *stream);
@@ -337,6 +342,10 @@ int spx_fshard_close(spx_fshard *h);
  * stored on every rank, keys exchanged over NVLink, ratio partials in (grid barrier 2), level recorded}.
  * Synchronises `stream`.  No reference counterpart. */
 int spx_fused_debug_stamps(const void *d_work, int32_t n, int64_t ld, uint64_t *h_out, int32_t capacity, void *stream);
+/* Developer aid: with SPX_RESIDENT_STAMPS=1 in the environment the L2-resident persistent kernels accumulate clock64()
+ * cycles per phase of a pivot (thread 0 of CTA 0); h_out16[0..14] = the sums over the last launch in the order of the
+ * kernel's pc.mark(k) calls (csrc/spx_resident.cu), h_out16[15] = pivots applied.  No reference counterpart. */
+int spx_resident_debug(uint64_t *h_out16);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,7 @@ PIVOT, OPTIMAL, INCORRECT, NOCONV, CAP, PEER_TIMEOUT = 1, 0, -1, -2, -3, -4
 RULE_REFERENCE, RULE_DANTZIG = 0, 1
 OPT_UPDATE_KERNEL, OPT_TILED_MIN_BLOCKS, OPT_PIPE_ORDER, OPT_PIPE_GRID, OPT_TILED_ROWS, OPT_FUSE_DEPTH = 1, 2, 3, 4, 5, 6
 OPT_FUSE_MIN_BLOCKS, OPT_FUSE_PRICING, OPT_FUSE_LOOKAHEAD, OPT_FUSE_VARIANT, OPT_FUSE_TILE_ROWS, OPT_FUSE_PAIRS = 7, 8, 9, 10, 11, 12
+OPT_SHARD_THREADS, OPT_SHARD_CTAS, OPT_RESIDENT_VARIANT = 13, 14, 15
 RULES = {"reference": RULE_REFERENCE, "bland": RULE_REFERENCE, "dantzig": RULE_DANTZIG}
 
 # the two ValueError texts of pick_element(), /root/reference/src/simplex.py:89,139
@@ -112,6 +113,7 @@ SIGNATURES = {
     "spx_fshard_read": (ctypes.c_int, [_vp, _vp, _pi32, _vp]),
     "spx_fshard_close": (ctypes.c_int, [_vp]),
     "spx_fused_debug_stamps": (ctypes.c_int, [_vp, _i32, _i64, ctypes.POINTER(ctypes.c_uint64), _i32, _vp]),
+    "spx_resident_debug": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint64)]),
 }
 
 _lib = None

@@ -36,7 +36,7 @@ int64_t fused_workspace_bytes(int, int64_t);
 cudaError_t fused_pass(double *, double *, double *, double *, int, int, int64_t, int, int, int, int, int, spx_state *,
                        void *, int32_t *, int32_t *, int32_t *, cudaStream_t);
 cudaError_t fused_solve_passes(double *, double *, double *, double *, int, int, int64_t, int, spx_state *, void *,
-                               int32_t *, int32_t *, int32_t *, int64_t, int, int, bool, cudaStream_t);
+                               int32_t *, int32_t *, int32_t *, int64_t, int, int, int, cudaStream_t);
 cudaError_t fused_solo_sync();
 int64_t get_option(int);
 int     set_option(int, int64_t);
@@ -397,11 +397,11 @@ int spx_solve(double *d_A0, double *d_A1, double *d_b0, double *d_b1, int32_t n,
             // look-ahead (option): the pricing of pass q+1 runs on a side stream during the update of pass q.
             // Off by default on ONE GPU: pricing is 4 % of a pass there and the overlap costs as much as it
             // hides (measured 3.14 k vs 3.21 k pivots/s); on by default in the column-sharded loop.
-            const bool la = spx_launch::get_option(SPX_OPT_FUSE_LOOKAHEAD) == 1;
-            if (la) {
+            const int la = (int)spx_launch::get_option(SPX_OPT_FUSE_LOOKAHEAD);      // 1 per-pass kernels, 2 persistent engine
+            if (la == 1 || la == 2) {
                 if (check(spx_launch::fused_solve_passes(d_A0, d_A1, d_b0, d_b1, n, m, ld, rule, d_state, d_work, d_rowlab,
                                                          d_collab, d_trace, k, F,
-                                                         (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS), true, s),
+                                                         (int)spx_launch::get_option(SPX_OPT_FUSE_MIN_BLOCKS), la, s),
                           "fused pass launch")) return -1;
             } else {
                 int64_t left = k;

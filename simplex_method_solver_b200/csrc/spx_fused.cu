@@ -223,7 +223,17 @@ struct CoopScratch {
     unsigned int       pad;
     unsigned long long bcast;                   // ... and the epoch of the last exchange result CTA 0 published
     unsigned long long stamp[FUSE_MAX + 1][STAMPS];   // debug: ns at level start / after sync 1 / column stored / keys
-};                                              //        exchanged / ratio partials synced / level done (thread 0)
+                                                //        exchanged / ratio partials synced / level done (thread 0)
+    // persistent pricing engine (shard_price_kernel with npass > 1 passes per launch): the device-side hand-shake
+    // between the ONE pricing kernel of an enqueue call and the update kernels of its passes
+    unsigned long long plan_ready;              // the last pass number whose plan / ROW planes / COL planes are published
+    unsigned long long upd_done;                // the last pass number whose update kernel has finished (its last CTA)
+    unsigned long long p_alive;                 // first pass number of the pricing kernel that is resident right now
+    unsigned int       upd_ctr;                 // CTAs of the running update kernel that are done
+    unsigned int       abort;                   // a device-side wait of this call timed out: every later wait gives up at once
+    unsigned long long go;                      // CTA 0 -> grid: (pass number << 1) | (its table is ready: 1, gave up: 0)
+    unsigned long long pass_stamp[4];           // debug: ns at the last pass's start / table ready / first level / published
+};
 
 struct CoopArgs {
     PriceArgs  a;
@@ -446,8 +456,15 @@ struct ShardArgs {
     int64_t col0;
     unsigned long long seq;      // pass number (1, 2, ...): the value the flags of this pass carry
     unsigned char *xbox[XB_MAX_RANKS];   // every rank's XBOX mapped into this process ([rank] = local)
-    const PlanHeader *prev_plan;         // look-ahead: the plan of the pass whose update is still running (else null)
-    const double *prev_ROWS;             //             and its ROW planes
+    // the passes of this launch: pass q (0 <= q < npass) has number seq + q, writes plans[(seq + q) & 1] /
+    // rows[(seq + q) & 1] and prices min(depth, pivots left) levels.  with_prev: the pass before the first one
+    // is still being applied by its update kernel (look-ahead); within a launch every later pass has one.
+    // persistent (npass may be > 1): the kernel stays resident for the whole enqueue call — it waits for the
+    // update of pass q - 2 on cs->upd_done and publishes pass q on cs->plan_ready (see fused_run).
+    PlanHeader *plans[2];
+    double *rows[2];
+    int npass, depth, with_prev, persistent, wait_updates;
+    int64_t pivots;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -507,7 +524,7 @@ __device__ __forceinline__ bool wait_seq(const unsigned long long *flag, unsigne
 // lexicographic minimum.  Returns through sel[0] = global column (or SPX_NONE), sel[1] = owner rank,
 // sel[2] = 0 / 1 (timeout).
 __device__ void exchange_keys(const ShardArgs &sa, const XBoxLayout &XL, int kpar, int level, int kind,
-                              unsigned long long kh, unsigned long long kl, int *sel) {
+                              unsigned long long kh, unsigned long long kl, unsigned long long seq, int *sel) {
     const int tid = threadIdx.x, R = sa.R;
     level += kpar * (FUSE_MAX + 1);                     // the slot set of this pass parity
     __shared__ int s_to;
@@ -520,11 +537,11 @@ __device__ void exchange_keys(const ShardArgs &sa, const XBoxLayout &XL, int kpa
         slot[0] = kh; slot[1] = kl;
         unsigned long long *fl = reinterpret_cast<unsigned long long *>(box + XL.kflag_off) +
                                  ((int64_t)level * 2 + kind) * R + sa.rank;
-        st_release_sys(fl, sa.seq);                      // release: the two key words are visible first
+        st_release_sys(fl, seq);                         // release: the two key words are visible first
         // ... and wait for rank `tid`'s key in MY box
         const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(sa.xbox[sa.rank] + XL.kflag_off) +
                                          ((int64_t)level * 2 + kind) * R + tid;
-        if (!wait_seq(mine, sa.seq)) s_to = 1;
+        if (!wait_seq(mine, seq)) s_to = 1;
     }
     __syncthreads();
     if (tid == 0) {
@@ -541,6 +558,51 @@ __device__ void exchange_keys(const ShardArgs &sa, const XBoxLayout &XL, int kpa
     }
 }
 
+// The device-side waits of the persistent pricing engine.  Every one of them gives up after ENGINE_WAIT_NS or as soon
+// as another wait of the same call has given up (cs->abort): a lost hand-shake ends the call with SPX_PEER_TIMEOUT
+// (and a table that is no longer meaningful) instead of hanging the GPU.
+constexpr unsigned long long ENGINE_WAIT_NS = 30000000000ull;
+__device__ __forceinline__ unsigned int ld_relaxed_gpu_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread: until *flag >= v (acquire, gpu scope: the writer is another kernel of THIS device); false = gave up
+__device__ __forceinline__ bool spin_ge_or_abort(const unsigned long long *flag, unsigned long long v, unsigned int *abort) {
+    const unsigned long long t0 = gtimer_ns();
+    for (unsigned it = 0;; ++it) {
+        if (ld_acquire_gpu_u64(flag) >= v) return true;
+        if ((it & 15u) == 15u) {
+            if (ld_relaxed_gpu_u32(abort) != 0u) return false;
+            if (gtimer_ns() - t0 > ENGINE_WAIT_NS) { atomicExch(abort, 1u); return false; }
+        }
+        __nanosleep(40);
+    }
+}
+// the whole CTA: true when *flag >= v was observed by thread 0
+__device__ __forceinline__ bool cta_wait_ge(const unsigned long long *flag, unsigned long long v, unsigned int *abort) {
+    int ok = 1;
+    if (threadIdx.x == 0) ok = spin_ge_or_abort(flag, v, abort) ? 1 : 0;
+    return __syncthreads_and(ok) != 0;
+}
+// pricing kernel, pass `seq`: CTA 0 waits for the update of pass seq - 2 and tells the grid how that went, so that
+// every CTA takes the same decision (they meet at grid barriers right after)
+__device__ __forceinline__ bool grid_gate_update_done(CoopScratch *cs, unsigned long long seq) {
+    int ok = 1;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            ok = spin_ge_or_abort(&cs->upd_done, seq - 2ull, &cs->abort) ? 1 : 0;
+            __threadfence();
+            st_release_gpu_u64(&cs->go, (seq << 1) | (unsigned long long)ok);
+        } else {
+            unsigned long long g;
+            while (((g = ld_acquire_gpu_u64(&cs->go)) >> 1) != seq) __nanosleep(40);
+            ok = (int)(g & 1ull);
+        }
+    }
+    return __syncthreads_and(ok) != 0;
+}
+
 __global__ void __launch_bounds__(COOP_THREADS, 1)
 shard_price_kernel(ShardArgs sa) {
     cg::grid_group grid = cg::this_grid();
@@ -552,41 +614,82 @@ shard_price_kernel(ShardArgs sa) {
     __shared__ LevelDiv s_lvl[2 * FUSE_MAX];
     __shared__ double s_scal[2 * FUSE_MAX];
     __shared__ const double *s_rowp[2 * FUSE_MAX];       // per level: its ROW plane (local columns)
+    __shared__ const double *s_colp[2 * FUSE_MAX];       // per level: the winner's COL plane in MY box
     const int n = a.n, m = a.m, tid = threadIdx.x;
     const int G = gridDim.x, gtid = blockIdx.x * blockDim.x + tid, gn = G * blockDim.x;
     const int64_t ld = a.ld, cbd = a.cbd, col0 = sa.col0;
     const XBoxLayout XL = xbox_layout(cbd, sa.R);
+    int *gsel = &ca.cs->idx[FUSE_MAX][0];               // CTA 0 -> grid: {column, owner, timeout} of the last exchange
+
+    // the solve's state travels in registers from pass to pass (every thread derives the same values); the device
+    // copy is written once per pass by thread 0 for the host and for the next launch
+    int status = (int)a.st->status;
+    int cur = (int)a.st->reserved[0] & 1;                // the buffer the next pass's INPUT table lives in
+    int64_t npiv = a.st->npiv;
+    const int64_t cap = a.st->max_pivots;
+    int64_t left = sa.pivots;
+    int prev_f = 0;                                      // levels of the previous pass of THIS launch
+
+    if (sa.persistent) {
+        // every CTA of this kernel is resident now: the update kernels of this call may start (they spin on
+        // plan_ready while they occupy the other SMs — had they started first, this kernel could not be placed)
+        grid.sync();
+        if (gtid == 0) st_release_gpu_u64(&ca.cs->p_alive, sa.seq);
+    }
+
+    for (int q = 0; q < sa.npass; ++q) {
+    const unsigned long long seq = sa.seq + (unsigned long long)q;
+    const int hq = (int)(seq & 1ull);
+    PlanHeader *plan = sa.plans[hq];
+    double *ROWS = sa.rows[hq];
+    const bool has_prev = (q > 0) || sa.with_prev;
+    const PlanHeader *prev_plan = has_prev ? sa.plans[hq ^ 1] : nullptr;
+    const double *prev_ROWS = has_prev ? sa.rows[hq ^ 1] : nullptr;
+    const int F = (int)(left < (int64_t)sa.depth ? left : (int64_t)sa.depth);
+    left -= F;
+    const bool last_pass = (q == sa.npass - 1);
+    if (last_pass && gtid == 0) ca.cs->pass_stamp[0] = gtimer_ns();
+    // the update of pass q - 2 read plan[hq], ROWS[hq] and wrote the table this pass gathers from
+    if (sa.persistent && sa.wait_updates && q >= 2 && !grid_gate_update_done(ca.cs, seq) && status == SPX_PIVOT)
+        status = SPX_PEER_TIMEOUT;
+    if (last_pass && gtid == 0) ca.cs->pass_stamp[1] = gtimer_ns();
+
     // COL planes are TRIPLE-buffered by pass number: with look-ahead a fast rank can be pricing pass q+1
     // (storing into every rank's planes) while a slow rank's update of pass q-1 still reads its planes —
     // the slow rank's pricing of pass q, which the fast rank had to wait for, runs concurrently with that
     // update.  Pass q+2 cannot start anywhere before every rank's update q-1 has finished.
-    const int par = (int)(sa.seq % 3ull);
-    const int par_prev = (int)((sa.seq + 2ull) % 3ull);
-    const int kpar = (int)(sa.seq & 1ull);               // key / flag slots: double-buffered by pass parity
+    const int par = (int)(seq % 3ull);
+    const int par_prev = (int)((seq + 2ull) % 3ull);
+    const int kpar = (int)(seq & 1ull);                  // key / flag slots: double-buffered by pass parity
     // this pass's COLS planes in MY box: plane (level l, source rank g) at COLS + (l * R + g) * cbd
     double *COLS = reinterpret_cast<double *>(sa.xbox[sa.rank] + XL.cols_off) + (int64_t)par * FUSE_MAX * sa.R * cbd;
-    __shared__ const double *s_colp[2 * FUSE_MAX];       // per level: the winner's COL plane in MY box
-    int *gsel = &ca.cs->idx[FUSE_MAX][0];               // CTA 0 -> grid: {column, owner, timeout} of the last exchange
 
-    if (a.st->status != SPX_PIVOT) {                     // uniform over the grid AND over the ranks
-        if (gtid == 0) a.plan->f = 0;
-        return;
+    if (status != SPX_PIVOT) {                           // uniform over the grid AND over the ranks
+        if (gtid == 0) {
+            plan->f = 0;
+            a.st->status = status;                       // (a wait that gave up above ends the solve here)
+            if (sa.persistent) { __threadfence(); st_release_gpu_u64(&ca.cs->plan_ready, seq); }
+        }
+        prev_f = 0;
+        continue;
     }
     // cur = the buffer this pass's INPUT table lives in (it may still be under construction by the
     // previous pass's update); the cells are gathered from the last MATERIALISED table: the other buffer
     // when np levels of the previous pass are pending, cur itself otherwise
-    const int cur = (int)a.st->reserved[0] & 1;
-    const int np = (sa.prev_plan != nullptr) ? sa.prev_plan->f : 0;
+    // np: within a launch the previous pass's f is known to every thread (its plan->f store is not ordered
+    // before this pass by any grid barrier); across launches it comes from memory
+    const int np = (prev_plan == nullptr) ? 0 : (q > 0 ? prev_f : __ldcg(&prev_plan->f));
     const double *A = a.A[np > 0 ? (cur ^ 1) : cur];
-    const int64_t npiv0 = a.st->npiv, cap = a.st->max_pivots;
+    const int64_t npiv0 = npiv;
+    __syncthreads();                                     // the previous pass's readers of s_lvl / s_colp / s_rowp are done
     if (tid < np) {
-        const int64_t cl = (int64_t)sa.prev_plan->lvl[tid].c - col0;
-        s_lvl[tid].r = sa.prev_plan->lvl[tid].r;
+        const int64_t cl = (int64_t)__ldcg(&prev_plan->lvl[tid].c) - col0;
+        s_lvl[tid].r = __ldcg(&prev_plan->lvl[tid].r);
         s_lvl[tid].c = (cl >= 0 && cl < m) ? (int)cl : -1;
-        s_lvl[tid].d = pivot_div_prepare(sa.prev_plan->lvl[tid].p);
-        s_rowp[tid] = sa.prev_ROWS + (int64_t)tid * ld;
+        s_lvl[tid].d = pivot_div_prepare(__ldcg(&prev_plan->lvl[tid].p));
+        s_rowp[tid] = prev_ROWS + (int64_t)tid * ld;
         s_colp[tid] = reinterpret_cast<const double *>(sa.xbox[sa.rank] + XL.cols_off) +
-                      (((int64_t)par_prev * FUSE_MAX + tid) * sa.R + sa.prev_plan->owner[tid]) * cbd;
+                      (((int64_t)par_prev * FUSE_MAX + tid) * sa.R + __ldcg(&prev_plan->owner[tid])) * cbd;
     }
     __syncthreads();
 
@@ -596,20 +699,21 @@ shard_price_kernel(ShardArgs sa) {
             if (k % 4 == 0) ca.cs->key[k / 4] = ~0ull;
         }
     grid.sync();
+    if (last_pass && gtid == 0) ca.cs->pass_stamp[2] = gtimer_ns();
 
-    int status = SPX_PIVOT, f = 0, last_r = -1, last_c = -1, phase1 = 0;
+    int f = 0, last_r = -1, last_c = -1, phase1 = 0;
     double last_p = 0.0;
-    for (int i = 0; i <= a.F; ++i) {
+    for (int i = 0; i <= F; ++i) {
         // ---------------- phase A (see coop_price_kernel): running b (replicated), local f row shard,
         // local shard of ROW_{i-1}, first-negative folds
         double *bout = ca.bv[i & 1];
         int bneg = SPX_NONE, fneg = SPX_NONE;
         unsigned long long fkey = ~0ull;
         if (i == 0) {
-            for (int t = gtid; t < n; t += gn) { const double v = a.b[cur][t]; bout[t] = v; if (v < 0.0) bneg = min(bneg, t); }
+            for (int t = gtid; t < n; t += gn) { const double v = __ldcg(&a.b[cur][t]); bout[t] = v; if (v < 0.0) bneg = min(bneg, t); }
             for (int j = gtid; j < m; j += gn) {
                 // np > 0: the previous pricing left the running f row at exactly this table
-                const double v = (np > 0) ? a.frow[j] : A[(int64_t)n * ld + j];
+                const double v = (np > 0) ? __ldcg(&a.frow[j]) : __ldcg(&A[(int64_t)n * ld + j]);
                 a.frow[j] = v;
                 if (v < 0.0) { fneg = min(fneg, j); const unsigned long long k = orderable(v); fkey = k < fkey ? k : fkey; }
             }
@@ -626,19 +730,19 @@ shard_price_kernel(ShardArgs sa) {
             }
             if (tid < np + i - 1) s_scal[tid] = __ldcg(s_colp[tid] + L.r);
             __syncthreads();
-            double *ROWL = a.ROWS + (int64_t)(i - 1) * ld;
+            double *ROWL = ROWS + (int64_t)(i - 1) * ld;
             const double *rowp = A + (int64_t)L.r * ld;
             for (int j = gtid; j < ld; j += gn) {
                 if (j >= m) { ROWL[j] = 0.0; continue; }
-                const double rv = replay_levels<true>(rowp[j], L.r, j, np + i - 1, s_lvl, s_rowp, j, s_scal);
+                const double rv = replay_levels<true>(__ldcg(rowp + j), L.r, j, np + i - 1, s_lvl, s_rowp, j, s_scal);
                 ROWL[j] = rv;
-                const double fj = a.frow[j];
+                const double fj = __ldcg(&a.frow[j]);
                 const double v = (j == L.c) ? pivot_div(fc, L.d) : cell_update(fj, L.d, rv, fc);
                 a.frow[j] = v;
                 if (v < 0.0) { fneg = min(fneg, j); const unsigned long long k = orderable(v); fkey = k < fkey ? k : fkey; }
             }
         }
-        if (i == a.F) { f = a.F; break; }
+        if (i == F) { f = F; break; }
         if (gtid == 0) ca.cs->stamp[i][0] = gtimer_ns();
         bneg = block_min_int(bneg, s);
         fneg = block_min_int(fneg, s);
@@ -665,7 +769,7 @@ shard_price_kernel(ShardArgs sa) {
             const double *row = A + (int64_t)r1 * ld;
             int loc = SPX_NONE;
             for (int j = gtid; j < m; j += gn) {
-                const double v = replay_levels<true>(row[j], r1, j, np + i, s_lvl, s_rowp, j, s_scal);
+                const double v = replay_levels<true>(__ldcg(row + j), r1, j, np + i, s_lvl, s_rowp, j, s_scal);
                 if (v > 0.0) { loc = j; break; }
             }
             loc = block_min_int(loc, s);
@@ -676,7 +780,7 @@ shard_price_kernel(ShardArgs sa) {
             const unsigned long long best = __ldcg(&ca.cs->key[i]);
             int loc = SPX_NONE;
             for (int j = gtid; j < m; j += gn) {
-                const double v = a.frow[j];
+                const double v = __ldcg(&a.frow[j]);
                 if (v < 0.0 && orderable(v) == best) { loc = j; break; }
             }
             loc = block_min_int(loc, s);
@@ -692,7 +796,7 @@ shard_price_kernel(ShardArgs sa) {
             __syncthreads();
             const int64_t plane = (((int64_t)par * FUSE_MAX + i) * sa.R + sa.rank) * cbd;
             for (int t = gtid; t <= n; t += gn) {
-                const double w = replay_levels<false>(A[(int64_t)t * ld + cloc], t, cloc, np + i, s_lvl, s_colp, t, s_scal);
+                const double w = replay_levels<false>(__ldcg(&A[(int64_t)t * ld + cloc]), t, cloc, np + i, s_lvl, s_colp, t, s_scal);
                 for (int g = 0; g < sa.R; ++g)
                     (reinterpret_cast<double *>(sa.xbox[g] + XL.cols_off) + plane)[t] = w;
             }
@@ -702,7 +806,7 @@ shard_price_kernel(ShardArgs sa) {
         // the flag it releases to the peers), exchanges, and BROADCASTS the result under a per-level epoch the
         // other CTAs spin on — an all-to-one plus a one-to-all instead of two all-to-alls.
         {
-            const unsigned long long epoch = sa.seq * (unsigned long long)(2 * FUSE_MAX) + (unsigned long long)i + 1ull;
+            const unsigned long long epoch = seq * (unsigned long long)(2 * FUSE_MAX) + (unsigned long long)i + 1ull;
             __threadfence_system();
             __syncthreads();
             if (blockIdx.x == 0) {
@@ -714,7 +818,7 @@ shard_price_kernel(ShardArgs sa) {
                 }
                 __syncthreads();
                 exchange_keys(sa, XL, kpar, i, kind, (cloc == SPX_NONE) ? ~0ull : kh,
-                              (cloc == SPX_NONE) ? ~0ull : (unsigned long long)(col0 + cloc), gsel);
+                              (cloc == SPX_NONE) ? ~0ull : (unsigned long long)(col0 + cloc), seq, gsel);
                 __syncthreads();
                 if (tid == 0) { __threadfence(); st_release_gpu_u64(&ca.cs->bcast, epoch); }
             } else if (tid == 0) {
@@ -732,18 +836,18 @@ shard_price_kernel(ShardArgs sa) {
         const int clocal = (cl64 >= 0 && cl64 < m) ? (int)cl64 : -1;
         if (tid == 0) {
             s_colp[np + i] = COLS + ((int64_t)i * sa.R + owner) * cbd;
-            s_rowp[np + i] = a.ROWS + (int64_t)i * ld;
+            s_rowp[np + i] = ROWS + (int64_t)i * ld;
         }
         __syncthreads();
 
         // ---------------- ratio fold on the received column (every rank, identical) (:107-136)
         const double *COLi = s_colp[np + i];
-        Ratio q = ratio_identity();
+        Ratio qr = ratio_identity();
         if (r1 < 0)
-            for (int t = gtid; t < n; t += gn) ratio_accumulate(q, t, __ldcg(COLi + t), bout[t]);
-        q = block_ratio_reduce(q, s);
+            for (int t = gtid; t < n; t += gn) ratio_accumulate(qr, t, __ldcg(COLi + t), bout[t]);
+        qr = block_ratio_reduce(qr, s);
         Ratio *part = ca.part + (int64_t)i * G;
-        if (tid == 0) part[blockIdx.x] = q;
+        if (tid == 0) part[blockIdx.x] = qr;
         grid.sync();
         if (gtid == 0) ca.cs->stamp[i][4] = gtimer_ns();
         int r;
@@ -773,8 +877,8 @@ shard_price_kernel(ShardArgs sa) {
             s_lvl[np + i].r = r; s_lvl[np + i].c = clocal; s_lvl[np + i].d = pivot_div_prepare(p);
             if (blockIdx.x == 0) {
                 ca.cs->stamp[i][5] = gtimer_ns();
-                a.plan->lvl[i].r = r; a.plan->lvl[i].c = c; a.plan->lvl[i].p = p;       // GLOBAL column in the plan
-                a.plan->owner[i] = owner;
+                plan->lvl[i].r = r; plan->lvl[i].c = c; plan->lvl[i].p = p;             // GLOBAL column in the plan
+                plan->owner[i] = owner;
                 const int32_t tmp = a.rowlab[c]; a.rowlab[c] = a.collab[r]; a.collab[r] = tmp;
                 if (a.trace) { a.trace[2 * (npiv0 + i)] = r; a.trace[2 * (npiv0 + i) + 1] = c; }
             }
@@ -783,20 +887,27 @@ shard_price_kernel(ShardArgs sa) {
         last_r = r; last_c = c; last_p = p; phase1 = (r1 >= 0);
     }
 
+    // ---------------- publish the pass: b after f levels, plan, state — then (persistent) release the update
     if (f > 0) {
-        grid.sync();
+        grid.sync();                                     // every CTA's ROW planes and running b are complete
         const double *bfin = ca.bv[f & 1];
         for (int t = gtid; t < n; t += gn) a.b[cur ^ 1][t] = __ldcg(bfin + t);
     }
     if (gtid == 0) {
-        a.plan->f = f;
-        a.plan->src = cur;
+        plan->f = f;
+        plan->src = cur;
         spx_state *st = a.st;
         st->status = status; st->r = last_r; st->c = last_c; st->p = last_p;
         st->npiv = npiv0 + f; st->phase1 = phase1; st->slot = 0;
         st->hint_tag[0] = st->hint_tag[1] = -1;
         st->reserved[0] = (f > 0) ? (cur ^ 1) : cur;
+        if (sa.persistent) { __threadfence(); st_release_gpu_u64(&ca.cs->plan_ready, seq); }
+        if (last_pass) ca.cs->pass_stamp[3] = gtimer_ns();
     }
+    npiv = npiv0 + f;
+    prev_f = f;
+    if (f > 0) cur ^= 1;
+    }   // passes
 }
 
 // ---- the fused streaming update: one pass over the body applies plan->f levels -----------------
@@ -1049,11 +1160,10 @@ __device__ __forceinline__ void lazy_level_np(double2 (&t)[FUP_UNROLL][NP], cons
     }
 }
 
-template <int NP, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-update_lazy_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R, int rw,
-                   const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
-                   const double *__restrict__ COLS) {
+template <int NP, int THREADS>
+__device__ __forceinline__ void lazy_strip(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R,
+                                           int rw, const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
+                                           const double *__restrict__ COLS) {
     using G = LazyGeom<NP>;
     const int f = plan->f;
     if (f <= 0) return;
@@ -1237,6 +1347,33 @@ update_lazy_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd
     }
 }
 
+// SYNC = false: the update of one pass, launched after its pricing kernel in stream order.
+// SYNC = true : the update of pass `seq` next to a PERSISTENT pricing kernel (fused_run, price engine 2): the kernel is
+//   launched ahead of time; every CTA waits until the pricing kernel has published the pass (plan, ROW planes, COL
+//   planes: cs->plan_ready >= seq, acquire) and the last CTA to finish publishes cs->upd_done = seq (release), which
+//   the pricing of pass seq + 2 waits for before it gathers from the table written here.
+template <int NP, int THREADS, int MINB, bool SYNC>
+__global__ void __launch_bounds__(THREADS, MINB)
+update_lazy_kernel(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R, int rw,
+                   const PlanHeader *__restrict__ plan, const double *__restrict__ ROWS,
+                   const double *__restrict__ COLS, CoopScratch *cs, unsigned long long seq) {
+    bool go = true;
+    if (SYNC) go = cta_wait_ge(&cs->plan_ready, seq, &cs->abort);
+    if (go) lazy_strip<NP, THREADS>(A0, A1, n, m, ld, cbd, col0, R, rw, plan, ROWS, COLS);
+    if (SYNC) {
+        __syncthreads();                                         // every warp's stores are issued
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int t = atomicAdd(&cs->upd_ctr, 1u);
+            if (t == gridDim.x - 1) {
+                cs->upd_ctr = 0u;                                // the next update kernel starts after this one
+                __threadfence();
+                st_release_gpu_u64(&cs->upd_done, seq);
+            }
+        }
+    }
+}
+
 // adversarial self-test of the lazy guard: chain k of `count` starts from cell t[k] and goes through F levels
 // (p[l], ROW value rj[k][l], COL value ci[k][l]); out_lazy = the kernel's policy (raw chain, range test on the
 // output, guarded redo when it fails), out_ref = the guarded chain.  The host compares bits.
@@ -1324,43 +1461,56 @@ int64_t fused_workspace_bytes(int n, int64_t ld) { return carve_work(nullptr, n,
 
 int64_t get_option(int key);
 
+// One-time per-device configuration of every update_lazy_kernel instantiation (dynamic shared-memory limit).  It also
+// LOADS them: with CUDA's lazy module loading the first use of a kernel may need a context-wide synchronisation, which
+// never returns while a persistent kernel that waits for that very kernel is resident (see preload_engine_kernels).
+static cudaError_t configure_lazy_kernels() {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (configured[dev]) return cudaSuccess;
+    cudaFuncAttributes fa;
+#define SPX_LZ_CFG1(NP, TH, MB, SY) \
+    if ((e = cudaFuncSetAttribute(update_lazy_kernel<NP, TH, MB, SY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (TH / 32) * LazyGeom<NP>::WARP_BYTES)) != cudaSuccess) return e; \
+    if ((e = cudaFuncGetAttributes(&fa, update_lazy_kernel<NP, TH, MB, SY>)) != cudaSuccess) return e;
+#define SPX_LZ_CFG(NP, TH, MB) SPX_LZ_CFG1(NP, TH, MB, false) SPX_LZ_CFG1(NP, TH, MB, true)
+    SPX_LZ_CFG(1, 256, 2) SPX_LZ_CFG(1, 256, 3) SPX_LZ_CFG(2, 128, 2) SPX_LZ_CFG(2, 128, 3)
+#undef SPX_LZ_CFG
+#undef SPX_LZ_CFG1
+    configured[dev] = true;
+    return cudaSuccess;
+}
+
 // The fused update launch.  SPX_OPT_FUSE_VARIANT 0 (default): update_lazy_kernel; 1: round 1's update_fused_kernel
 // (returns cudaErrorNotSupported here and the caller launches it).  SPX_OPT_FUSE_TILE_ROWS: tile height of the lazy
 // kernel (0 = 32; a multiple of 8 <= 256); minb: resident CTAs per SM its register budget targets (0 = 3).
 static cudaError_t launch_update_variant(double *A0, double *A1, int n, int m, int64_t ld, int64_t cbd, int64_t col0, int R,
                                          const PlanHeader *plan, const double *ROWS, const double *COLS, int minb,
-                                         bool persistent, cudaStream_t stream) {
+                                         CoopScratch *sync, unsigned long long seq, cudaStream_t stream) {
     if ((int)get_option(SPX_OPT_FUSE_VARIANT) == 1) return cudaErrorNotSupported;
     int rw = (int)get_option(SPX_OPT_FUSE_TILE_ROWS);
     if (rw <= 0) rw = 128;
     int np = (int)get_option(SPX_OPT_FUSE_PAIRS);
     if (np <= 0) np = 2;
     if (minb <= 0) minb = np == 2 ? 3 : 2;
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    cudaError_t e = configure_lazy_kernels();
     if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    if (!configured[dev]) {
-#define SPX_LZ_CFG(NP, TH, MB) \
-        if ((e = cudaFuncSetAttribute(update_lazy_kernel<NP, TH, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (TH / 32) * LazyGeom<NP>::WARP_BYTES)) != cudaSuccess) return e;
-        SPX_LZ_CFG(1, 256, 2) SPX_LZ_CFG(1, 256, 3) SPX_LZ_CFG(2, 128, 2) SPX_LZ_CFG(2, 128, 3)
-#undef SPX_LZ_CFG
-        configured[dev] = true;
-    }
     const int sc = 64 * np, wpc = (np == 2) ? 4 : 8;        // strip width, warps per CTA
     const int64_t nwork = (int64_t)((m + sc - 1) / sc) * ((n + 1 + rw - 1) / rw);      // warp-sized pieces
     if (m <= 0 || nwork == 0) return cudaSuccess;           // a shard without columns only prices
     if (nwork + 64 >= (int64_t)1 << 31) return cudaErrorInvalidValue;
-    (void)persistent;
     const unsigned grid = (unsigned)((nwork + wpc - 1) / wpc);
-#define SPX_LZ_RUN(NP, TH, MB) \
-    update_lazy_kernel<NP, TH, MB><<<grid, TH, (TH / 32) * LazyGeom<NP>::WARP_BYTES, stream>>>(A0, A1, n, m, ld, cbd, col0, R, \
-                                                                                               rw, plan, ROWS, COLS)
+#define SPX_LZ_RUN1(NP, TH, MB, SY) \
+    update_lazy_kernel<NP, TH, MB, SY><<<grid, TH, (TH / 32) * LazyGeom<NP>::WARP_BYTES, stream>>>(A0, A1, n, m, ld, cbd, col0, R, \
+                                                                                                   rw, plan, ROWS, COLS, sync, seq)
+#define SPX_LZ_RUN(NP, TH, MB) do { if (sync) SPX_LZ_RUN1(NP, TH, MB, true); else SPX_LZ_RUN1(NP, TH, MB, false); } while (0)
     if (np == 2) { if (minb == 2) SPX_LZ_RUN(2, 128, 2); else SPX_LZ_RUN(2, 128, 3); }
     else         { if (minb == 3) SPX_LZ_RUN(1, 256, 3); else SPX_LZ_RUN(1, 256, 2); }
 #undef SPX_LZ_RUN
+#undef SPX_LZ_RUN1
     spx_host::count_launch();
     return cudaGetLastError();
 }
@@ -1421,7 +1571,7 @@ cudaError_t fused_pass(double *A0, double *A1, double *b0, double *b1, int n, in
     if (e != cudaSuccess) return e;
     if (phase != 2) spx_host::count_launch();
     if (phase == 1) return cudaSuccess;
-    if ((e = launch_update_variant(A0, A1, n, m, ld, cbd, col0, 1, plan, ROWS, COLS, minb, true, stream)) != cudaErrorNotSupported)
+    if ((e = launch_update_variant(A0, A1, n, m, ld, cbd, col0, 1, plan, ROWS, COLS, minb, nullptr, 0ull, stream)) != cudaErrorNotSupported)
         return e;
     static bool configured_dev[64] = {};
     bool &configured = configured_dev[spx_host::device_slot()];
@@ -1477,18 +1627,23 @@ void fused_ctx_destroy(FusedCtx &c) {
     c.side = nullptr;
 }
 
-static cudaError_t launch_shard_price(const FusedCtx &c, const FusedWork &w, int F, int h, bool with_prev,
-                                      cudaStream_t stream) {
+// One pricing launch: `npass` passes starting at pass number c.seq (the caller has already advanced it to the
+// first pass).  npass == 1, persistent == false: the classic one-kernel-per-pass form.
+static cudaError_t launch_shard_price(const FusedCtx &c, const FusedWork &w, int depth, int64_t pivots, int npass,
+                                      bool with_prev, bool persistent, cudaStream_t stream) {
     ShardArgs sa;
     PriceArgs &a = sa.ca.a;
     a.A[0] = c.A[0]; a.A[1] = c.A[1]; a.b[0] = c.b[0]; a.b[1] = c.b[1];
-    a.n = c.n; a.m = c.m_loc; a.ld = c.ld; a.cbd = colbuf_doubles(c.n); a.rule = c.rule; a.F = F;
-    a.st = c.st; a.plan = w.plan[h]; a.ROWS = w.ROWS[h]; a.COLS = nullptr; a.frow = w.frow; a.bvec = w.bvec;
+    a.n = c.n; a.m = c.m_loc; a.ld = c.ld; a.cbd = colbuf_doubles(c.n); a.rule = c.rule; a.F = depth;
+    a.st = c.st; a.plan = nullptr; a.ROWS = nullptr; a.COLS = nullptr; a.frow = w.frow; a.bvec = w.bvec;
     a.rowlab = c.rowlab; a.collab = c.collab; a.trace = c.trace;
     sa.ca.bv[0] = w.bvec; sa.ca.bv[1] = w.bvec2; sa.ca.cs = w.cs; sa.ca.part = w.part;
     sa.rank = c.rank; sa.R = c.R; sa.col0 = c.col0; sa.seq = c.seq;
-    sa.prev_plan = with_prev ? w.plan[h ^ 1] : nullptr;
-    sa.prev_ROWS = with_prev ? w.ROWS[h ^ 1] : nullptr;
+    for (int h = 0; h < 2; ++h) { sa.plans[h] = w.plan[h]; sa.rows[h] = w.ROWS[h]; }
+    sa.npass = npass; sa.depth = depth; sa.pivots = pivots;
+    sa.with_prev = with_prev ? 1 : 0;
+    sa.persistent = persistent ? 1 : 0;
+    sa.wait_updates = (c.m_loc > 0) ? 1 : 0;             // a shard without columns launches no update kernels
     for (int g = 0; g < XB_MAX_RANKS; ++g) sa.xbox[g] = g < c.R ? static_cast<unsigned char *>(c.xbox[g]) : nullptr;
     if (g_shard_ctas < 0) {
         int dev = 0, coop = 0, per_sm = 0;
@@ -1508,7 +1663,10 @@ static cudaError_t launch_shard_price(const FusedCtx &c, const FusedWork &w, int
     // SPX_OPT_SHARD_CTAS caps the grid (one CTA per SM): the SMs the pricing kernel does NOT occupy keep streaming
     // the update of the previous pass while it runs
     const int cap_ctas = (int)get_option(SPX_OPT_SHARD_CTAS);
-    const int max_ctas = (cap_ctas > 0 && cap_ctas < g_shard_ctas) ? cap_ctas : g_shard_ctas;
+    int max_ctas = (cap_ctas > 0 && cap_ctas < g_shard_ctas) ? cap_ctas : g_shard_ctas;
+    // a persistent engine keeps its SMs (a 512-thread CTA takes a whole one) while it waits for update kernels: it must
+    // leave them most of the GPU, or they could never finish
+    if (persistent && max_ctas > g_shard_ctas / 4) max_ctas = g_shard_ctas / 4 > 0 ? g_shard_ctas / 4 : 1;
     G = G > max_ctas ? max_ctas : (G < 1 ? 1 : G);
     void *args[] = {&sa};
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)shard_price_kernel, dim3(G), dim3(threads), args, 0, stream);
@@ -1516,9 +1674,7 @@ static cudaError_t launch_shard_price(const FusedCtx &c, const FusedWork &w, int
     return e;
 }
 
-static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, int h, int minb, bool persistent,
-                                       cudaStream_t stream) {
-    const int slot3 = (int)(c.seq % 3ull);               // the COL planes of this pass (c.seq = its pass number)
+static cudaError_t configure_round1_kernels() {
     static bool configured_dev[64] = {};
     bool &configured = configured_dev[spx_host::device_slot()];
     cudaError_t e;
@@ -1527,13 +1683,23 @@ static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, in
         if ((e = cudaFuncSetAttribute(update_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem))) != cudaSuccess) return e;
         configured = true;
     }
+    return cudaSuccess;
+}
+
+// `sync` != null: the update of pass c.seq next to a persistent pricing kernel (update_lazy_kernel<.., true>)
+static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, int h, int minb, CoopScratch *sync,
+                                       cudaStream_t stream) {
+    const int slot3 = (int)(c.seq % 3ull);               // the COL planes of this pass (c.seq = its pass number)
+    cudaError_t e = configure_round1_kernels();
+    if (e != cudaSuccess) return e;
     const int64_t cbd = colbuf_doubles(c.n);
     const XBoxLayout XL = xbox_layout(cbd, c.R);
     const double *COLS = reinterpret_cast<const double *>(static_cast<unsigned char *>(c.xbox[c.rank]) + XL.cols_off) +
                          (int64_t)slot3 * FUSE_MAX * c.R * cbd;
     if ((e = launch_update_variant(c.A[0], c.A[1], c.n, c.m_loc, c.ld, cbd, c.col0, c.R, w.plan[h], w.ROWS[h], COLS, minb,
-                                   persistent, stream)) != cudaErrorNotSupported)
+                                   sync, c.seq, stream)) != cudaErrorNotSupported)
         return e;
+    if (sync) return cudaErrorNotSupported;                  // round 1's kernel has no device-side hand-shake
     dim3 grid((unsigned)((c.m_loc + FUP_TC - 1) / FUP_TC), (unsigned)((c.n + 1 + FUP_TR - 1) / FUP_TR));
     if (grid.x == 0) return cudaSuccess;                     // a shard without columns only prices
     if (minb == 3)
@@ -1546,35 +1712,95 @@ static cudaError_t launch_fused_update(const FusedCtx &c, const FusedWork &w, in
     return cudaGetLastError();
 }
 
-// Enqueue `pivots` pivots as passes of `depth` (the last one shorter).
-//   lookahead == false : price q, update q, price q+1, ... on `s`.
-//   lookahead == true  : the pricing of pass q+1 runs on the side stream WHILE the update of pass q streams
-//       on `s`; it gathers from the table the running update reads and replays that pass's levels first
-//       (up to 2 x depth - 1 pending levels).  P_q waits for U_{q-2} (its table and its buffer set),
-//       U_q waits for P_q.
-cudaError_t fused_run(FusedCtx &c, int64_t pivots, int depth, int minb, bool lookahead, cudaStream_t s) {
+// one warp: returns once the persistent pricing kernel of the call that starts at pass `seq0` is resident (or gives
+// up after ENGINE_WAIT_NS and raises cs->abort: the update kernels behind it then skip their bodies)
+__global__ void wait_engine_kernel(CoopScratch *cs, unsigned long long seq0) {
+    if (threadIdx.x == 0) spin_ge_or_abort(&cs->p_alive, seq0, &cs->abort);
+}
+
+// Everything the persistent engine runs next to itself must be loaded BEFORE it starts: CUDA loads kernels lazily, and
+// loading one may synchronise the context — behind a resident kernel that is waiting for the kernel being loaded.
+// (Seen on 2 GPUs in fresh processes: the first update launch blocked on the host until the engine's wait for it
+// timed out; in the single-process tests earlier cases had already loaded every kernel.)
+static cudaError_t preload_engine_kernels() {
+    static bool loaded[64] = {};
+    const int dev = spx_host::device_slot();
+    if (loaded[dev]) return cudaSuccess;
+    cudaError_t e = configure_lazy_kernels();
+    if (e != cudaSuccess) return e;
+    if ((e = configure_round1_kernels()) != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    if ((e = cudaFuncGetAttributes(&fa, wait_engine_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, shard_price_kernel)) != cudaSuccess) return e;
+    loaded[dev] = true;
+    return cudaSuccess;
+}
+
+// Enqueue `pivots` pivots as passes of `depth` (the last one shorter).  `engine`:
+//   0  no look-ahead: price q, update q, price q+1, ... on `s`.
+//   1  look-ahead, one pricing kernel per pass: the pricing of pass q+1 runs on the side stream WHILE the update
+//      of pass q streams on `s`; it gathers from the table the running update reads and replays that pass's
+//      levels first (up to 2 x depth - 1 pending levels).  P_q waits for U_{q-2} (its table and its buffer set),
+//      U_q waits for P_q — both through events.
+//   2  look-ahead with a PERSISTENT pricing engine: ONE cooperative pricing kernel prices every pass of the call
+//      and stays on its SMs (33 of 148 at n = 16384) from the first pass to the last; all update kernels are
+//      enqueued at once behind it and the same two dependencies go through device flags (cs->plan_ready,
+//      cs->upd_done).  What it removes from the critical chain of a pricing-bound run (8 GPUs: the update of a
+//      4096-column shard is shorter than the pricing of 8 levels): a cooperative launch + two events per pass, and
+//      the race for SMs at every pass boundary — a per-pass pricing kernel that loses it waits for a whole wave of
+//      update CTAs (~100 us) to retire before all of its CTAs are resident, and the slowest rank sets everybody's
+//      pace through the key exchange.  The update kernels must not start before the engine is resident (they
+//      would fill every SM and spin on plan_ready for ever): a one-warp kernel on `s` waits for cs->p_alive first.
+cudaError_t fused_run(FusedCtx &c, int64_t pivots, int depth, int minb, int engine, cudaStream_t s) {
     if (depth < 1) depth = 1;
     if (depth > FUSE_MAX) depth = FUSE_MAX;
+    if (pivots <= 0) return cudaSuccess;
     const FusedWork w = carve_work(c.work, c.n, c.ld);
     cudaError_t e;
-    if (lookahead) {
+    if (engine == 2 && (int)get_option(SPX_OPT_FUSE_VARIANT) == 1) engine = 1;
+    if (engine != 0) {
         if ((e = cudaEventRecord(c.ev_start, s)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(c.side, c.ev_start, 0)) != cudaSuccess) return e;
+    }
+    if (engine == 2) {
+        if ((e = preload_engine_kernels()) != cudaSuccess) return e;
+        const int64_t npass64 = (pivots + depth - 1) / depth;
+        if (npass64 > (1 << 30)) return cudaErrorInvalidValue;
+        const int npass = (int)npass64;
+        ++c.seq;                                             // the first pass of this call
+        const unsigned long long seq0 = c.seq;
+        if ((e = cudaMemsetAsync(&w.cs->abort, 0, sizeof(unsigned int), c.side)) != cudaSuccess) return e;
+        if ((e = launch_shard_price(c, w, depth, pivots, npass, false, true, c.side)) != cudaSuccess) return e;
+        wait_engine_kernel<<<1, 32, 0, s>>>(w.cs, seq0);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        spx_host::count_launch();
+        for (int q = 0; q < npass; ++q) {
+            if (q > 0) ++c.seq;
+            if ((e = launch_fused_update(c, w, (int)(c.seq & 1ull), minb, w.cs, s)) != cudaSuccess) return e;
+        }
+        // The engine's last writes (state, labels, b) are ordered before whatever follows on `s`.  The event is
+        // recorded only NOW, after the update kernels have been submitted: streams share a few hardware work queues
+        // (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default; a process that has initialised NCCL owns dozens of streams),
+        // a queue is consumed in submission order, and "record after the engine ends" submitted ahead of the update
+        // kernels on the same queue would hold them back until the engine ends — while the engine waits for them
+        // (first seen on 2 GPUs: every run stopped at the first upd_done wait with SPX_PEER_TIMEOUT).
+        if ((e = cudaEventRecord(c.ev_priced[0], c.side)) != cudaSuccess) return e;
+        return cudaStreamWaitEvent(s, c.ev_priced[0], 0);
     }
     int64_t left = pivots;
     for (int q = 0; left > 0; ++q) {
         const int F = (int)(left < depth ? left : depth);
         const int h = (int)(++c.seq & 1ull);
-        if (lookahead) {
+        if (engine == 1) {
             if (q >= 2 && (e = cudaStreamWaitEvent(c.side, c.ev_upd[h], 0)) != cudaSuccess) return e;
-            if ((e = launch_shard_price(c, w, F, h, q > 0, c.side)) != cudaSuccess) return e;
+            if ((e = launch_shard_price(c, w, F, F, 1, q > 0, false, c.side)) != cudaSuccess) return e;
             if ((e = cudaEventRecord(c.ev_priced[h], c.side)) != cudaSuccess) return e;
             if ((e = cudaStreamWaitEvent(s, c.ev_priced[h], 0)) != cudaSuccess) return e;
-            if ((e = launch_fused_update(c, w, h, minb, false, s)) != cudaSuccess) return e;
+            if ((e = launch_fused_update(c, w, h, minb, nullptr, s)) != cudaSuccess) return e;
             if ((e = cudaEventRecord(c.ev_upd[h], s)) != cudaSuccess) return e;
         } else {
-            if ((e = launch_shard_price(c, w, F, h, false, s)) != cudaSuccess) return e;
-            if ((e = launch_fused_update(c, w, h, minb, true, s)) != cudaSuccess) return e;
+            if ((e = launch_shard_price(c, w, F, F, 1, false, false, s)) != cudaSuccess) return e;
+            if ((e = launch_fused_update(c, w, h, minb, nullptr, s)) != cudaSuccess) return e;
         }
         left -= F;
     }
@@ -1587,7 +1813,7 @@ static FusedCtx g_solo[64];
 
 cudaError_t fused_solve_passes(double *A0, double *A1, double *b0, double *b1, int n, int m, int64_t ld, int rule,
                                spx_state *st, void *work, int32_t *rowlab, int32_t *collab, int32_t *trace,
-                               int64_t pivots, int depth, int minb, bool lookahead, cudaStream_t s) {
+                               int64_t pivots, int depth, int minb, int engine, cudaStream_t s) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -1598,7 +1824,7 @@ cudaError_t fused_solve_passes(double *A0, double *A1, double *b0, double *b1, i
     c.n = n; c.m_loc = m; c.rule = rule; c.rank = 0; c.R = 1; c.ld = ld; c.col0 = 0;
     c.st = st; c.work = work; c.rowlab = rowlab; c.collab = collab; c.trace = trace;
     c.xbox[0] = carve_work(work, n, ld).xbox1;
-    return fused_run(c, pivots, depth, minb, lookahead, s);
+    return fused_run(c, pivots, depth, minb, engine, s);
 }
 
 // the caller must not free or reuse a workspace while side-stream work on it may be pending
@@ -1627,7 +1853,7 @@ int xbox_max_ranks() { return XB_MAX_RANKS; }
 // ---- C ABI of the column-sharded fused loop (declared in include/spx_b200.h) -------------------
 struct spx_fshard {
     spx_launch::FusedCtx c;
-    bool lookahead;
+    int engine;          // 0 no look-ahead, 1 look-ahead with one pricing kernel per pass, 2 persistent pricing engine
 };
 
 extern "C" {
@@ -1662,15 +1888,15 @@ int spx_fshard_open(spx_fshard **out, int32_t rank, int32_t nranks, int32_t n, i
     }
     c.seq = 0;
     c.side = nullptr;
-    h->lookahead = true;
+    h->engine = 1;
     if (spx_host::check(spx_launch::fused_ctx_streams(c), "side stream")) { delete h; return -1; }
     *out = h;
     return 0;
 }
 
 int spx_fshard_set_lookahead(spx_fshard *h, int32_t on) {
-    if (!h) return -2;
-    h->lookahead = on != 0;
+    if (!h || on < 0 || on > 2) return -2;
+    h->engine = on;
     return 0;
 }
 
@@ -1679,7 +1905,7 @@ int spx_fshard_set_lookahead(spx_fshard *h, int32_t on) {
 int spx_fshard_enqueue(spx_fshard *h, int64_t pivots, int32_t depth, void *stream) {
     if (!h || pivots < 0) { spx_host::set_error("spx_fshard_enqueue: bad arguments"); return -2; }
     if (depth <= 0) depth = 8;
-    return spx_host::check(spx_launch::fused_run(h->c, pivots, depth, 0, h->lookahead,
+    return spx_host::check(spx_launch::fused_run(h->c, pivots, depth, 0, h->engine,
                                                  reinterpret_cast<cudaStream_t>(stream)), "fused shard passes");
 }
 

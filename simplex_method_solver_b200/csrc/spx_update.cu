@@ -447,6 +447,7 @@ int set_option(int key, int64_t value) {
     case SPX_OPT_FUSE_PAIRS:       if (value < 0 || value > 2) return -1; break;
     case SPX_OPT_SHARD_THREADS:    if (value < 0 || value > 512 || value % 32 || value == 32) return -1; break;
     case SPX_OPT_SHARD_CTAS:       if (value < 0 || value > 4096) return -1; break;
+    case SPX_OPT_RESIDENT_VARIANT: if (value < 0 || value > 1) return -1; break;
     default: return -1;
     }
     g_opt[key] = value;

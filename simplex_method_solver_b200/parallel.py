@@ -32,6 +32,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes
+import os
 from typing import Optional
 
 import numpy as np
@@ -437,13 +438,31 @@ class FusedShardedTableau(ShardedTableau):
     winning pivot column from inside the kernel over NVLink peer memory, then every rank streams its
     own columns ONCE for all of them.  Same pivots and bits as every other loop."""
 
+    # ranks from which the pricing of 8 levels outlasts the update of a cfg4-sized shard (measured: 8)
+    PERSISTENT_FROM_WORLD = 8
+
     def __init__(self, n: int, m: int, rank: int, world: int, device, trace_capacity: int = 0,
-                 group=None, rule: int = N.RULE_REFERENCE, depth: int = 8, lookahead: bool = True):
+                 group=None, rule: int = N.RULE_REFERENCE, depth: int = 8, lookahead=True):
+        """lookahead: False — price, update, price, ...; True — the pricing of pass q+1 overlaps the update of
+        pass q, as one pricing kernel per pass below PERSISTENT_FROM_WORLD ranks and as the persistent pricing
+        engine from there on; "per-pass" / "persistent" force one of the two (every rank must choose the same)."""
         super().__init__(n, m, rank, world, device, trace_capacity=trace_capacity, group=group, rule=rule,
                          lookahead=False)
         L = N.lib()
         self.depth = int(depth)
-        self.price_ahead = bool(lookahead)
+        if lookahead == "persistent":
+            self.price_engine = 2
+        elif lookahead == "per-pass":
+            self.price_engine = 1
+        elif lookahead:
+            forced = os.environ.get("SPX_PRICE_ENGINE", "")          # "per-pass" | "persistent": override the default
+            if forced in ("per-pass", "persistent"):
+                self.price_engine = 2 if forced == "persistent" else 1
+            else:
+                self.price_engine = 2 if world >= self.PERSISTENT_FROM_WORLD else 1
+        else:
+            self.price_engine = 0
+        self.price_ahead = self.price_engine != 0
         dev = self.device
         wbytes = int(L.spx_fused_workspace_bytes(self.n, max(self.m_loc, 1)))
         self.work = torch.zeros(wbytes // 8 + 16, dtype=torch.float64, device=dev)
@@ -454,7 +473,7 @@ class FusedShardedTableau(ShardedTableau):
                    rule, self.A[0].data_ptr(), self.A[1].data_ptr(), self.b[0].data_ptr(), self.b[1].data_ptr(),
                    self.state.data_ptr(), self.work.data_ptr(), self.work.numel() * 8, self.rowlab.data_ptr(),
                    self.collab.data_ptr(), N.ptr(self.trace), self.xbox.ptrs)
-            N.call("spx_fshard_set_lookahead", self.handle, int(self.price_ahead))
+            N.call("spx_fshard_set_lookahead", self.handle, self.price_engine)
         self._cur = 0
 
     def load(self, rows, function, max_pivots: int):

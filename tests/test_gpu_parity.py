@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 
 class loop_mode:
-    """'fused-coop' = the fused loop of spx_solve with look-ahead pricing (side stream, replay through the
+    """'fused-engine' = the same with the persistent pricing engine; 'fused-coop' = the fused loop of spx_solve with look-ahead pricing (side stream, replay through the
     previous pass's pending levels) switched on; every other name passes through."""
 
     def __init__(self, name):
@@ -26,9 +26,15 @@ class loop_mode:
         if self.name == "fused-coop":                  # the fused loop of spx_solve with look-ahead pricing on
             assert N.lib().spx_set_option(9, 1) == 0
             return "fused"
+        if self.name == "fused-engine":                # ... with the persistent pricing engine (one kernel per call)
+            assert N.lib().spx_set_option(9, 2) == 0
+            return "fused"
         if self.name == "fused-gpuwide":               # ... with the whole-GPU cooperative pricing kernel forced on
             assert N.lib().spx_set_option(8, 2) == 0
             return "fused"
+        if self.name == "resident-ahead":              # the L2-resident kernel with look-ahead pricing inside the CTA
+            assert N.lib().spx_set_option(15, 1) == 0
+            return "resident"
         if isinstance(self.name, str) and self.name.startswith("fused-x"):   # "fused-x<variant>-<rows>[-<minb>[-<pairs>]]":
             parts = self.name[len("fused-x"):].split("-")                    # update kernel schedule
             assert N.lib().spx_set_option(10, int(parts[0])) == 0
@@ -40,10 +46,12 @@ class loop_mode:
 
     def __exit__(self, *a):
         from simplex_method_solver_b200 import _native as N
-        if self.name == "fused-coop":
+        if self.name in ("fused-coop", "fused-engine"):
             N.lib().spx_set_option(9, 0)
         if self.name == "fused-gpuwide":
             N.lib().spx_set_option(8, 0)
+        if self.name == "resident-ahead":
+            N.lib().spx_set_option(15, 0)
         if isinstance(self.name, str) and self.name.startswith("fused-x"):
             for k in (10, 11, 7, 12):
                 N.lib().spx_set_option(k, 0)
@@ -136,7 +144,8 @@ def test_problem_files_feed_the_batched_solver(spx):
 
 # --------------------------------------------------------------------------- all golden cases
 @pytest.mark.parametrize("lookahead,chunk", [(False, 7), (True, 7), (True, 4), (True, 1), ("resident", 7), (None, 5),
-                                             ("fused", 7), ("fused", 3), ("fused-coop", 7), ("fused-gpuwide", 5)])
+                                             ("fused", 7), ("fused", 3), ("fused-coop", 7), ("fused-gpuwide", 5),
+                                             ("fused-engine", 7), ("fused-engine", 40), ("resident-ahead", 7)])
 def test_all_reference_cases_streaming_solver(spx, ref_cases, lookahead, chunk):
     """solve(): device-side loop, classic (pick k, update k, ...) and look-ahead (pivot k+1 priced
     from table k on a side stream while update k runs); trace, ending, labels, final table bits."""
@@ -234,7 +243,7 @@ def test_lookahead_state_feeds_the_step_api_and_resumes(spx, mode):
     assert sol.x.tobytes() == ref.x.tobytes()
 
 
-@pytest.mark.parametrize("lookahead", [False, True, "resident", "fused", "fused-coop", "fused-gpuwide", "warp"])
+@pytest.mark.parametrize("lookahead", [False, True, "resident", "fused", "fused-coop", "fused-gpuwide", "fused-engine", "warp"])
 def test_dantzig_rule_every_loop_against_the_restated_oracle(spx, dantzig_cases, lookahead):
     """rule='dantzig' (extension: most negative f cell, lowest index on ties) in every CUDA loop —
     classic, look-ahead, L2-resident, fused (one-CTA, cooperative, whole-GPU pricing), warp-resident batched —
@@ -342,7 +351,7 @@ def test_pick_update_bit_exact_ragged_shapes(spx, n, m):
         assert dev.read_state().npiv == npiv
 
 
-@pytest.mark.parametrize("mode", ["resident", "fused", "fused-coop", "fused-gpuwide"])
+@pytest.mark.parametrize("mode", ["resident", "resident-ahead", "fused", "fused-coop", "fused-gpuwide", "fused-engine"])
 @pytest.mark.parametrize("n,m", [(1, 2), (3, 1), (7, 15), (9, 17), (64, 512), (65, 513), (130, 1030), (257, 100), (40, 2049)])
 def test_resident_and_fused_loops_bit_exact_ragged_shapes(spx, n, m, mode):
     with loop_mode(mode) as mode_:
@@ -603,7 +612,7 @@ def test_fused_pass_entry_point_both_pricing_kernels(spx, n, m, depth, pricing):
 
 @pytest.mark.parametrize("n,m,kind,depth", [(20, 700, "dense", 8), (33, 2500, "dense", 3), (12, 1300, "smallint", 8),
                                             (9, 40, "smallint", 5), (300, 700, "dense", 8)])
-@pytest.mark.parametrize("ahead", [True, False])
+@pytest.mark.parametrize("ahead", ["per-pass", "persistent", False])
 def test_fused_sharded_loop_single_rank(spx, n, m, kind, depth, ahead):
     """The column-sharded fused loop (cooperative pricing with the in-kernel exchange) with ONE rank:
     the whole code path except the cross-rank selection, against the oracle."""
@@ -635,7 +644,7 @@ def test_fused_sharded_loop_single_rank(spx, n, m, kind, depth, ahead):
 
 
 # --------------------------------------------------------------------------- BASELINE configs
-@pytest.mark.parametrize("lookahead", [False, True, "resident", "fused", "fused-coop"])
+@pytest.mark.parametrize("lookahead", [False, True, "resident", "resident-ahead", "fused", "fused-coop", "fused-engine"])
 def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests, lookahead):
     with loop_mode(lookahead) as mode_:
         _cfg2_full(spx, cfg_digests, mode_)

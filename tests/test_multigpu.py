@@ -41,8 +41,9 @@ def _worker(rank, world, port, n, m, seed, cap, mode, kind, out):
     try:
         from simplex_method_solver_b200 import parallel as P
         rows, c = _make_lp(n, m, seed, kind)
-        if mode == "fused":
-            sh = P.FusedShardedTableau(n, m, rank, world, dev, trace_capacity=cap + 8, depth=5)
+        if mode in ("fused", "fused-persistent"):
+            sh = P.FusedShardedTableau(n, m, rank, world, dev, trace_capacity=cap + 8, depth=5,
+                                       lookahead="persistent" if mode == "fused-persistent" else "per-pass")
         elif mode == "p2p":
             sh = P.PeerShardedTableau(n, m, rank, world, dev, trace_capacity=cap + 8)
         else:
@@ -57,7 +58,7 @@ def _worker(rank, world, port, n, m, seed, cap, mode, kind, out):
                         "trace": sh.trace[: int(st.npiv)].cpu().numpy().copy(),
                         "rowlab": sh.rowlab.cpu().numpy().copy(), "collab": sh.collab[:n].cpu().numpy().copy()}))
         dist.barrier()
-        if mode in ("p2p", "fused"):
+        if mode in ("p2p", "fused", "fused-persistent"):
             sh.close()
     finally:
         dist.destroy_process_group()
@@ -68,7 +69,7 @@ def _worker(rank, world, port, n, m, seed, cap, mode, kind, out):
 # all four exchange modes green (profiles/r2/r2a_multigpu_extended_2gpu_summary.txt); they are no longer gated.
 
 
-@pytest.mark.parametrize("mode", ["fused", "p2p", "nccl", "nccl-ahead"])
+@pytest.mark.parametrize("mode", ["fused", "fused-persistent", "p2p", "nccl", "nccl-ahead"])
 @pytest.mark.parametrize("n,m,cap,kind", [(300, 2600, 150, "dense"), (64, 1024, 400, "dense"),
                                           (9, 40, 60, "dense"),            # ranks >= 1 own no columns
                                           (12, 1300, 60, "smallint"), (20, 1100, 80, "smallint"),
