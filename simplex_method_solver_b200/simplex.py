@@ -19,6 +19,15 @@ Differences from the reference, all opt-in or unavoidable:
     large tableaus need no list-of-lists; inputs are never mutated.
   * ``solve()`` returns the trace / x / objective without per-pivot snapshots,
     which the reference cannot avoid (it deep-copies the table per pivot, :198).
+  * ``engine="sharded"``: one process per GPU (torchrun); every rank constructs
+    the same ``SimplexMethod`` and calls ``solve()`` — the body is split into
+    column blocks over the ranks of ``group`` (the default process group) and
+    pivoted by the column-sharded fused loop (``parallel.FusedShardedTableau``:
+    pricing inside a cooperative kernel with an NVLink peer-memory exchange per
+    pivot).  b, labels, trace, x and the objective are replicated, so
+    ``solve()``, ``find_optimum()``, ``f()``, ``row``/``column`` behave as on one
+    GPU; the step API and ``get_solution()``/``table`` (a snapshot per pivot of a
+    table no rank holds) raise ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -64,8 +73,10 @@ def _ragged(flat: np.ndarray, n: int, m: int):
 
 
 class SimplexMethod:
+    SHARDED_TRACE_MAX = 1 << 22           # pivots a sharded solve can trace (8 B each)
+
     def __init__(self, constraints, function, *, max_pivots: int = 1_000_000,
-                 rule: str = "reference", device=None, engine: str = "auto"):
+                 rule: str = "reference", device=None, engine: str = "auto", group=None):
         rows, c = as_rows_function(constraints, function)
         self.n = rows.shape[0]                               # :26
         self.m = rows.shape[1] - 1                           # :27
@@ -75,21 +86,80 @@ class SimplexMethod:
         self.column = ['y' + str(k) for k in range(1, self.n + 1)] + ['f']    # :31,:33
         if rule not in N.RULES:
             raise ValueError(f"unknown rule {rule!r}")
-        if engine not in ("auto", "warp", "stream"):
+        if engine not in ("auto", "warp", "stream", "sharded"):
             raise ValueError(f"unknown engine {engine!r}")
         self._rule = N.RULES[rule]
         self._engine = engine
         self._max_pivots = int(max_pivots)
         self._c = c
-        self._dev = DeviceTableau(self.n, self.m, device=device)
-        self._dev.load(rows, c)
         self._npiv = 0
         self._table_cache = None
+        self._sh = None
+        if engine == "sharded":
+            self._dev = None
+            self._open_sharded(rows, c, device, group)
+            return
+        self._dev = DeviceTableau(self.n, self.m, device=device)
+        self._dev.load(rows, c)
+
+    # ------------------------------------------------------------------ column-sharded engine
+    def _open_sharded(self, rows, c, device, group):
+        import torch.distributed as dist
+        from .parallel import FusedShardedTableau
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            rank, world = 0, 1
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self._trace_cap = min(self._max_pivots, self.SHARDED_TRACE_MAX)
+        self._sh = FusedShardedTableau(self.n, self.m, rank, world, device, trace_capacity=self._trace_cap + 64,
+                                       group=group, rule=self._rule)
+        self._sh.load(rows, c, max_pivots=self._max_pivots)
+        self._fn_dev = torch.from_numpy(np.ascontiguousarray(c, dtype=np.float64)).to(self._sh.device)
+        self._x_dev = torch.zeros(max(self.m, 1), dtype=torch.float64, device=self._sh.device)
+        self._obj_dev = torch.zeros(2, dtype=torch.float64, device=self._sh.device)
+
+    def _not_sharded(self, what):
+        if self._sh is not None:
+            raise NotImplementedError(f"{what} is not available with engine='sharded' (no rank holds the whole table); "
+                                      "use solve(), find_optimum(), f()")
+
+    def _solve_sharded(self, cap, chunk):
+        sh = self._sh
+        if self._npiv + cap > self._trace_cap:
+            raise ValueError(f"engine='sharded': {self._npiv + cap} pivots exceed the trace capacity {self._trace_cap} "
+                             "fixed at construction (max_pivots)")
+        total = self._npiv + cap
+        st = sh.read_state()                                 # (synchronises; keeps reserved[0] = the current buffer)
+        if int(st.max_pivots) != total or st.status == N.CAP:
+            st.max_pivots = total
+            if st.status == N.CAP:
+                st.status = N.PIVOT
+            sh.state.copy_(torch.from_numpy(np.frombuffer(bytes(st), dtype=np.int64).copy()))
+        status, npiv = sh.solve(total, check_every=max(int(chunk), 1))
+        self._npiv = int(npiv)
+        with torch.cuda.device(sh.device):
+            N.call("spx_extract", sh.b_current().data_ptr(), self.n, self.m, sh.collab.data_ptr(), self._fn_dev.data_ptr(),
+                   self._x_dev.data_ptr(), self._obj_dev.data_ptr(), torch.cuda.current_stream(sh.device).cuda_stream)
+        x = self._x_dev[: self.m].cpu().numpy()
+        obj = self._obj_dev.cpu().numpy()
+        rl, cl = sh.rowlab.cpu().numpy(), sh.collab[: self.n].cpu().numpy()
+        sol = Solution(int(status), self._npiv, sh.trace[: self._npiv].cpu().numpy(), x, float(obj[0]), float(obj[1]), rl, cl)
+        self._labels_from_codes(rl, cl)
+        return sol
+
+    def close(self):
+        """engine='sharded': release the peer-memory mappings (collective: every rank calls it)."""
+        if self._sh is not None:
+            self._sh.close()
+            self._sh = None
 
     # ------------------------------------------------------------------ views
     @property
     def table(self):
         """Current tableau as the reference's list of lists (:36-39), read back from HBM."""
+        self._not_sharded("table")
         if self._table_cache is None:
             self._table_cache = _ragged(self._dev.export_flat(self._npiv), self.n, self.m)
         return self._table_cache
@@ -111,7 +181,7 @@ class SimplexMethod:
         for name in ('x1', 'x2'):
             if name in self.column:
                 if b is None:
-                    b = self._dev.b_host(self._npiv)
+                    b = (self._sh.b_current().cpu().numpy() if self._sh is not None else self._dev.b_host(self._npiv))
                 out.append(float(b[self.column.index(name)]))
             else:
                 out.append(0)
@@ -119,6 +189,7 @@ class SimplexMethod:
 
     # ------------------------------------------------------------------ K1+K2
     def _pick_state(self):
+        self._not_sharded("the step API (pick_element / recalculate_matrix)")
         self._dev.pick(self._npiv, self._rule, sticky=False)
         st = self._dev.read_state()
         if st.status == N.CAP:
@@ -177,6 +248,7 @@ class SimplexMethod:
 
         snapshots=False keeps Info.table only on the last Info (large tableaus).
         """
+        self._not_sharded("get_solution()")
         result = [Info(self.row, self.column, self.table if snapshots else None,
                        None, None, 0, 0, 0)]                 # :181
         budget = self._max_pivots
@@ -267,6 +339,8 @@ class SimplexMethod:
         pick+update kernel pairs with one host read-back per `chunk` pivots.
         """
         cap = self._max_pivots if max_pivots is None else int(max_pivots)
+        if self._sh is not None:
+            return self._solve_sharded(cap, chunk if chunk != 64 else 4096)
         dev = self._dev
         start = self._npiv
         if trace:

@@ -643,6 +643,47 @@ def test_fused_sharded_loop_single_rank(spx, n, m, kind, depth, ahead):
         sh.close()
 
 
+@pytest.mark.parametrize("n,m,kind", [(20, 700, "dense"), (33, 2500, "dense"), (12, 1300, "smallint"), (9, 40, "smallint")])
+def test_simplexmethod_sharded_engine_reference_surface(spx, n, m, kind):
+    """SimplexMethod(..., engine="sharded"): the column-sharded fused loop behind the reference's surface.  One rank here
+    (the driver's box has one GPU; tests/test_multigpu.py runs the same call on 2-4 ranks): solve() in two instalments,
+    x / objective / labels / trace against the oracle, find_optimum() and f(), and the step API refusing politely."""
+    if kind == "dense":
+        rows, c = W.dense_lp(n, m, 3)
+    else:
+        rng = np.random.default_rng(5)
+        rows = np.hstack([rng.integers(-3, 4, (n, m)).astype(float), rng.integers(-2, 7, (n, 1)).astype(float)])
+        c = rng.integers(-3, 4, m).astype(float)
+    cap = 60
+    sm = spx.simplex.SimplexMethod(rows, c, engine="sharded", max_pivots=cap)
+    try:
+        first = oracle.solve(rows, c, max_pivots=13)
+        sol = sm.solve(max_pivots=13, chunk=5)
+        assert (sol.status, sol.npiv) == (first.status, first.npiv)
+        assert sol.trace.tolist() == first.trace.tolist()
+        o = oracle.solve(rows, c, max_pivots=cap)
+        if first.status == oracle.CAP:
+            sol = sm.solve(max_pivots=cap - 13)
+        assert (sol.status, sol.npiv) == (o.status, o.npiv)
+        assert sol.trace.tolist() == o.trace.tolist()
+        assert sol.rowlab.tolist() == o.rowlab.tolist() and sol.collab.tolist() == o.collab.tolist()
+        assert sol.x.tobytes() == o.x.tobytes()
+        assert float(sol.objective).hex() == float(o.objm).hex() and float(sol.obj2).hex() == float(o.obj2).hex()
+        x1, x2 = sm.find_optimum()
+        ref_sm_labels = [("x%d" % (v + 1)) if v < m else ("y%d" % (v - m + 1)) for v in o.collab.tolist()]
+        assert sm.column[:-1] == ref_sm_labels
+        want1 = float(o.x[0]) if "x1" in sm.column else 0
+        want2 = float(o.x[1]) if "x2" in sm.column else 0
+        assert (x1, x2) == (want1, want2)
+        assert sm.f(x1, x2) == c[0] * x1 + c[1] * x2
+        with pytest.raises(NotImplementedError):
+            sm.get_solution()
+        with pytest.raises(NotImplementedError):
+            sm.pick_element()
+    finally:
+        sm.close()
+
+
 # --------------------------------------------------------------------------- BASELINE configs
 @pytest.mark.parametrize("lookahead", [False, True, "resident", "resident-ahead", "fused", "fused-coop", "fused-engine"])
 def test_cfg2_dense_1000x2000_full_sequence(spx, cfg_digests, lookahead):

@@ -41,6 +41,19 @@ def _worker(rank, world, port, n, m, seed, cap, mode, kind, out):
     try:
         from simplex_method_solver_b200 import parallel as P
         rows, c = _make_lp(n, m, seed, kind)
+        if mode == "simplexmethod":
+            # the reference surface: every rank constructs the same SimplexMethod and calls solve()
+            from simplex_method_solver_b200.simplex import SimplexMethod
+            sm = SimplexMethod(rows, c, engine="sharded", max_pivots=cap)
+            sol = sm.solve()
+            sh = sm._sh
+            out.put((rank, {"status": int(sol.status), "npiv": int(sol.npiv), "col0": sh.col0,
+                            "body": sh.local_body().cpu().numpy().copy(), "b": sh.b_current().cpu().numpy().copy(),
+                            "trace": sol.trace.copy(), "rowlab": sol.rowlab.copy(), "collab": sol.collab.copy(),
+                            "x": sol.x.copy(), "objective": float(sol.objective), "labels": (list(sm.row), list(sm.column))}))
+            dist.barrier()
+            sm.close()
+            return
         if mode in ("fused", "fused-persistent"):
             sh = P.FusedShardedTableau(n, m, rank, world, dev, trace_capacity=cap + 8, depth=5,
                                        lookahead="persistent" if mode == "fused-persistent" else "per-pass")
@@ -69,7 +82,7 @@ def _worker(rank, world, port, n, m, seed, cap, mode, kind, out):
 # all four exchange modes green (profiles/r2/r2a_multigpu_extended_2gpu_summary.txt); they are no longer gated.
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused-persistent", "p2p", "nccl", "nccl-ahead"])
+@pytest.mark.parametrize("mode", ["fused", "fused-persistent", "p2p", "nccl", "nccl-ahead", "simplexmethod"])
 @pytest.mark.parametrize("n,m,cap,kind", [(300, 2600, 150, "dense"), (64, 1024, 400, "dense"),
                                           (9, 40, 60, "dense"),            # ranks >= 1 own no columns
                                           (12, 1300, 60, "smallint"), (20, 1100, 80, "smallint"),
@@ -106,6 +119,8 @@ def test_sharded_flow_on_real_gpus(mode, n, m, cap, kind):
         assert (g["status"], g["npiv"]) == (o.status, o.npiv), (mode, r, g["status"], g["npiv"], o.status, o.npiv)
         assert g["trace"].tolist() == o.trace.tolist()
         assert g["rowlab"].tolist() == o.rowlab.tolist() and g["collab"].tolist() == o.collab.tolist()
+        if mode == "simplexmethod":
+            assert g["x"].tobytes() == o.x.tobytes() and float(g["objective"]).hex() == float(o.objm).hex()
         body[:, g["col0"]: g["col0"] + g["body"].shape[1]] = g["body"]
         assert np.array_equal(g["b"].view(np.uint64), o.table[: n * (m + 1)].reshape(n, m + 1)[:, m].copy().view(np.uint64))
     ob = np.zeros((n + 1, m))
