@@ -827,13 +827,14 @@ def run_ours(args):
         # passes of 8 pivots: cooperative pricing with the in-kernel NVLink exchange, then ONE stream
         # over the local columns applies them all (csrc/spx_fused.cu).  If peer memory cannot be mapped on
         # this box (no CUDA IPC / P2P between the GPUs) every rank falls back to the NCCL all-gather flow.
-        # Pricing engines to try, in order: the persistent engine (one pricing kernel per run() call, device-flag
-        # hand-shakes with the update kernels — the default from 8 ranks on) and the per-pass engine (one pricing
-        # kernel per pass).  Each goes through the same two preflights before it may be timed.
+        # Pricing engines to try, in order: the per-pass engine (one pricing kernel per pass, the default) or, on
+        # request, the persistent engine first (one pricing kernel per run() call, device-flag hand-shakes with the
+        # update kernels).  Each goes through the same two preflights before it may be timed.
         if args.no_lookahead:
             engines = [False]
         elif args.price_engine == "auto":
-            engines = ["persistent", "per-pass"] if world >= FusedShardedTableau.PERSISTENT_FROM_WORLD else ["per-pass"]
+            engines = (["persistent", "per-pass"] if 0 < FusedShardedTableau.PERSISTENT_FROM_WORLD <= world
+                       else ["per-pass"])
         else:
             engines = [args.price_engine] + (["per-pass"] if args.price_engine == "persistent" else [])
         sh, peer_memory_ok, notes = None, True, []
@@ -1039,7 +1040,8 @@ def main():
     ap.add_argument("--shard-ctas", type=int, default=0,
                     help="N>1 fused loop: cap on the CTAs (= SMs) of the sharded pricing kernel (0 = library default)")
     ap.add_argument("--price-engine", default="auto", choices=["auto", "persistent", "per-pass"],
-                    help="N>1 fused loop: pricing engine (auto = persistent from 8 ranks on, else one kernel per pass)")
+                    help="N>1 fused loop: pricing engine (auto = one pricing kernel per pass; persistent = one per run() call, "
+                         "measured no faster: profiles/r2/r2q_r2r_persistent_engine.md)")
     ap.add_argument("--no-lookahead", action="store_true",
                     help="classic pick->update order instead of pricing pivot k+1 during update k")
     ap.add_argument("--max-connections", type=int, default=0,

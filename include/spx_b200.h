@@ -332,7 +332,8 @@ int spx_fshard_open(spx_fshard **out, int32_t rank, int32_t nranks, int32_t n, i
  * pricing engine — one cooperative pricing kernel per spx_fshard_enqueue call prices every pass and keeps its
  * SMs, the update kernels of all passes are enqueued behind it at once, and the two dependencies (update q
  * needs plan q; pricing q needs the table of update q-2) go through device flags instead of one cooperative
- * launch and two events per pass.  For pricing-bound shards (8 ranks on cfg4).  Every rank must use the same mode. */
+ * launch and two events per pass.  Opt-in: measured no faster than mode 1 on cfg4 (8 ranks 19.5 k vs 19.3 k pivots/s,
+ * 2 ranks 6.4 k vs 7.0 k).  Every rank must use the same mode. */
 int spx_fshard_set_lookahead(spx_fshard *h, int32_t on);
 int spx_fshard_enqueue(spx_fshard *h, int64_t pivots, int32_t depth, void *stream);
 int spx_fshard_read(spx_fshard *h, spx_state *h_state, int32_t *cur_buffer, void *stream);

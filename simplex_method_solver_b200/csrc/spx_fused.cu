@@ -1745,12 +1745,12 @@ static cudaError_t preload_engine_kernels() {
 //   2  look-ahead with a PERSISTENT pricing engine: ONE cooperative pricing kernel prices every pass of the call
 //      and stays on its SMs (33 of 148 at n = 16384) from the first pass to the last; all update kernels are
 //      enqueued at once behind it and the same two dependencies go through device flags (cs->plan_ready,
-//      cs->upd_done).  What it removes from the critical chain of a pricing-bound run (8 GPUs: the update of a
-//      4096-column shard is shorter than the pricing of 8 levels): a cooperative launch + two events per pass, and
-//      the race for SMs at every pass boundary — a per-pass pricing kernel that loses it waits for a whole wave of
-//      update CTAs (~100 us) to retire before all of its CTAs are resident, and the slowest rank sets everybody's
-//      pace through the key exchange.  The update kernels must not start before the engine is resident (they
-//      would fill every SM and spin on plan_ready for ever): a one-warp kernel on `s` waits for cs->p_alive first.
+//      cs->upd_done).  It takes one cooperative launch and two events per pass off the pricing chain.  Measured on
+//      cfg4 (profiles/r2/r2q_r2r_persistent_engine.md): 8 ranks 19.5 k pivots/s against 19.2-19.3 k with engine 1,
+//      2 ranks 6.4 k against 7.0 k (the engine never gives its SMs back to the update) — the launches were not what
+//      bounds a pricing-bound pass, the per-level chain is; engine 1 stays the default, this one is opt-in.
+//      The update kernels must not start before the engine is resident (they would fill every SM and spin on
+//      plan_ready while it cannot be placed): a one-warp kernel on `s` waits for cs->p_alive first.
 cudaError_t fused_run(FusedCtx &c, int64_t pivots, int depth, int minb, int engine, cudaStream_t s) {
     if (depth < 1) depth = 1;
     if (depth > FUSE_MAX) depth = FUSE_MAX;

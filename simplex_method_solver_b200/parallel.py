@@ -432,36 +432,45 @@ class PeerRegion:
                 self.local = 0
 
 
+def choose_price_engine(lookahead, world: int, forced: str = "", persistent_from: int = 0) -> int:
+    """Pricing engine of the column-sharded fused loop (spx_fshard_set_lookahead): 0 no look-ahead, 1 look-ahead with
+    one pricing kernel per pass, 2 look-ahead with the persistent pricing engine.  `lookahead`: False / True (= by
+    world size, unless $SPX_PRICE_ENGINE = `forced` names one) / "per-pass" / "persistent"."""
+    if lookahead == "persistent":
+        return 2
+    if lookahead == "per-pass":
+        return 1
+    if not lookahead:
+        return 0
+    if forced in ("per-pass", "persistent"):
+        return 2 if forced == "persistent" else 1
+    return 2 if 0 < persistent_from <= world else 1
+
+
 class FusedShardedTableau(ShardedTableau):
     """The column-sharded FUSED loop (csrc/spx_fused.cu, spx_fshard_*): passes of `depth` pivots —
     a whole-GPU cooperative kernel per rank prices them by lazy replay, exchanging keys and the
     winning pivot column from inside the kernel over NVLink peer memory, then every rank streams its
     own columns ONCE for all of them.  Same pivots and bits as every other loop."""
 
-    # ranks from which the pricing of 8 levels outlasts the update of a cfg4-sized shard (measured: 8)
-    PERSISTENT_FROM_WORLD = 8
+    # World size from which look-ahead uses the persistent pricing engine by default; 0 = never.  Measured on cfg4
+    # (profiles/r2/r2q_r2r_persistent_engine.md): 2 ranks 6.4 k pivots/s against 7.0 k with one pricing kernel per pass
+    # (the engine keeps 33 SMs for good; the per-pass kernel gives them back to the update between passes), 8 ranks
+    # 19.5 k against 19.2-19.3 k (the pricing chain of a level, not the launches around it, bounds the pass) — not a
+    # win anywhere, so it stays opt-in.
+    PERSISTENT_FROM_WORLD = 0
 
     def __init__(self, n: int, m: int, rank: int, world: int, device, trace_capacity: int = 0,
                  group=None, rule: int = N.RULE_REFERENCE, depth: int = 8, lookahead=True):
         """lookahead: False — price, update, price, ...; True — the pricing of pass q+1 overlaps the update of
-        pass q, as one pricing kernel per pass below PERSISTENT_FROM_WORLD ranks and as the persistent pricing
-        engine from there on; "per-pass" / "persistent" force one of the two (every rank must choose the same)."""
+        pass q, as one pricing kernel per pass (and, if PERSISTENT_FROM_WORLD is set, as the persistent pricing engine
+        from that many ranks on); "per-pass" / "persistent" force one of the two (every rank must choose the same)."""
         super().__init__(n, m, rank, world, device, trace_capacity=trace_capacity, group=group, rule=rule,
                          lookahead=False)
         L = N.lib()
         self.depth = int(depth)
-        if lookahead == "persistent":
-            self.price_engine = 2
-        elif lookahead == "per-pass":
-            self.price_engine = 1
-        elif lookahead:
-            forced = os.environ.get("SPX_PRICE_ENGINE", "")          # "per-pass" | "persistent": override the default
-            if forced in ("per-pass", "persistent"):
-                self.price_engine = 2 if forced == "persistent" else 1
-            else:
-                self.price_engine = 2 if world >= self.PERSISTENT_FROM_WORLD else 1
-        else:
-            self.price_engine = 0
+        self.price_engine = choose_price_engine(lookahead, world, os.environ.get("SPX_PRICE_ENGINE", ""),
+                                                self.PERSISTENT_FROM_WORLD)
         self.price_ahead = self.price_engine != 0
         dev = self.device
         wbytes = int(L.spx_fused_workspace_bytes(self.n, max(self.m_loc, 1)))

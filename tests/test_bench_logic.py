@@ -92,3 +92,14 @@ def test_late_lp_preflight_under_gloo(fail_rank):
     else:
         assert [g[1] for g in got] == [False, False]
         assert "injected failure" in got[fail_rank][3]
+
+
+def test_price_engine_choice():
+    """Which pricing engine the column-sharded fused loop uses (parallel.choose_price_engine): by world size unless forced."""
+    from simplex_method_solver_b200.parallel import choose_price_engine as ch
+    assert [ch(True, w) for w in (1, 2, 8, 16)] == [1, 1, 1, 1]                       # the shipped default: never
+    assert [ch(True, w, "", 8) for w in (1, 2, 4, 7, 8, 16)] == [1, 1, 1, 1, 2, 2]
+    assert ch(False, 8) == 0 and ch(False, 8, "persistent") == 0
+    assert ch("per-pass", 8) == 1 and ch("persistent", 1) == 2
+    assert ch(True, 2, "persistent") == 2 and ch(True, 8, "per-pass", 8) == 1 and ch(True, 8, "nonsense", 8) == 2
+    assert ch("persistent", 8, "per-pass") == 2           # an explicit argument beats the environment
