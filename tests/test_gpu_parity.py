@@ -786,6 +786,37 @@ def test_cfg4_16k_x_32k_prefix(spx, cfg_digests):
         assert hashlib.sha256(f.tobytes()).hexdigest() == g["marks"][str(mark)]["f_sha256"]
 
 
+def test_cfg4_whole_table_fused_2000_pivots_and_pivot_at_a_time_loop(spx):
+    """Every cell of the 4.3 GB tableau, not only b and f: the fused loop (8 pivots per pass) after 2000 pivots and the
+    pivot-at-a-time look-ahead loop (K3) after 100, each against the oracle's marks of tests/golden/cfg4_long.json —
+    pivot sha256, b / f sha256 and the 64-bit checksum of all 536,870,912 body cells (so the two loops agree with each
+    other through the oracle; tools/fused_check.py compares them directly)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg4_long.json")) as fh:
+        marks = json.load(fh)["marks"]
+    n, m = 16384, 32768
+    rows, c = W.dense_lp(n, m, 0)
+
+    def check(dev, npiv):
+        mk = marks[str(npiv)]
+        assert W.pivot_digest(dev.trace[:npiv].cpu().numpy()) == mk["pivot_sha256"]
+        cur = dev.cur(npiv)
+        assert hashlib.sha256(dev.b_host(npiv).tobytes()).hexdigest() == mk["b_sha256"]
+        assert hashlib.sha256(dev.A[cur, n, :m].cpu().numpy().tobytes()).hexdigest() == mk["f_sha256"]
+        assert W.body_checksum_torch(dev.A[cur, :n, :m]) == int(mk["body_checksum_u64"])
+
+    dev = spx.engine.DeviceTableau(n, m, trace_capacity=2100)
+    dev.load(rows, c, max_pivots=2100)
+    status, npiv = dev.solve(chunk=1000, stop_after=2000, lookahead="fused")
+    assert (status, npiv) == (spx.N.PIVOT, 2000)
+    check(dev, 2000)
+    dev.load(rows, c, max_pivots=200)
+    status, npiv = dev.solve(chunk=100, stop_after=100, lookahead=True)
+    assert (status, npiv) == (spx.N.PIVOT, 100)
+    check(dev, 100)
+
+
 # --------------------------------------------------------------------------- owner rank != 0 (kept last in this file)
 @pytest.mark.parametrize("exchange", ["copy", "mailbox"])
 @pytest.mark.parametrize("lookahead", [False, True])
