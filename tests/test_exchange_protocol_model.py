@@ -12,7 +12,10 @@ This is a MODEL of the stream/event/flag dependencies in csrc/spx_fused.cu (`fus
                                                             and its own Pw(r,q,*)
     Ub/Ue(r,q) update kernel of pass q on the main stream   needs Pe(r,q) [ev_priced] and Ue(r,q-1)
 
-Without look-ahead everything is one stream: Pb(r,q) also needs Ue(r,q-1).  The model is COARSER than
+Without look-ahead everything is one stream: Pb(r,q) also needs Ue(r,q-1).  The PERSISTENT pricing engine (one pricing
+kernel per call) has the same graph with device flags in place of the events plus the edge "the first update kernel waits
+until the engine is resident" (last two tests; the second one reproduces the deadlock met on hardware when CUDA's lazy
+kernel loading held the first update launch back until the engine had ended).  The model is COARSER than
 the kernels (one exchange per pass instead of one per level), i.e. it admits more interleavings, so
 "no violation in the model" carries over.  A read is a violation if, when the reading kernel ends, a
 location it read holds data of another pass (stores into one location are issued by one rank in pass
@@ -25,7 +28,8 @@ code uses and must find the overwrite with 2 (the race that motivated the third 
 import pytest
 
 
-def explore(ranks, passes, plane_slots, key_slots, lookahead):
+def explore(ranks, passes, plane_slots, key_slots, lookahead, extra_deps=None):
+    """extra_deps(event) -> further events it waits for (used to model the persistent engine's extra edges)."""
     R, Q = ranks, passes
     events = []
     for r in range(R):
@@ -59,6 +63,8 @@ def explore(ranks, passes, plane_slots, key_slots, lookahead):
                 d.append(("Ue", r, q - 1, -1))
         elif kind == "Ue":
             d.append(("Ub", r, q, -1))
+        if extra_deps is not None:
+            d.extend(extra_deps(e))
         return [index[x] for x in d]
 
     dep_mask = [sum(1 << i for i in set(deps(e))) for e in events]
@@ -130,3 +136,36 @@ def test_serial_passes_are_race_free(plane_slots):
 def test_one_key_slot_would_race():
     bad, _ = explore(2, 3, plane_slots=3, key_slots=1, lookahead=True)
     assert bad is not None and "keys" in bad
+
+
+# ---- the persistent pricing engine (fused_run engine 2): ONE pricing kernel per call walks Pb/Pe of every pass; the same
+# two dependencies travel through device flags (Ub(q) <- Pe(q): cs->plan_ready; Pb(q) <- Ue(q-2): cs->upd_done) instead of
+# events, plus one edge: the first update kernel may not start before the engine is resident (wait_engine_kernel).
+def _engine_edges(e):
+    kind, r, q, _ = e
+    return [("Pb", r, 1, -1)] if kind == "Ub" and q == 1 else []
+
+
+@pytest.mark.parametrize("ranks,passes", [(2, 5), (3, 4)])
+def test_persistent_engine_has_the_same_dependency_graph(ranks, passes):
+    bad, states = explore(ranks, passes, plane_slots=3, key_slots=2, lookahead=True, extra_deps=_engine_edges)
+    assert bad is None, bad
+    assert states > 1000
+
+
+def test_update_launches_held_back_until_the_engine_ends_deadlock():
+    """What happened on 2 GPUs in fresh processes (profiles/r2/r2q_r2r_persistent_engine.md): the host blocked inside the
+    first update launch (CUDA was loading that kernel lazily, which synchronises with the resident engine), i.e. Ub(1) could
+    not happen before the engine's last pass had ended — while the engine's third pass waits for Ue(1)."""
+    Q = 4
+
+    def blocked(e):
+        kind, r, q, _ = e
+        return _engine_edges(e) + ([("Pe", r, Q, -1)] if kind == "Ub" and q == 1 else [])
+
+    with pytest.raises(AssertionError, match="deadlocked"):
+        explore(2, Q, plane_slots=3, key_slots=2, lookahead=True, extra_deps=blocked)
+    # two passes per call could never show it: nothing in them waits for an update
+    bad, _ = explore(2, 2, plane_slots=3, key_slots=2, lookahead=True,
+                     extra_deps=lambda e: _engine_edges(e) + ([("Pe", e[1], 2, -1)] if e[0] == "Ub" and e[2] == 1 else []))
+    assert bad is None
